@@ -1,0 +1,62 @@
+// Library-wide plumbing: error text, device properties, the device-side fault flag.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace cvae {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+__device__ int g_fault_flag = 0;
+
+int* fault_flag() {
+    static thread_local int* ptr[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!ptr[dev]) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_fault_flag) != cudaSuccess) return nullptr;
+        ptr[dev] = (int*)p;
+    }
+    return ptr[dev];
+}
+
+}  // namespace cvae
+
+extern "C" const char* cvae_last_error(void) { return cvae::g_err; }
+extern "C" int cvae_version(void) { return 100; }
+
+extern "C" int cvae_check_device_fault(void* stream) {
+    int* p = cvae::fault_flag();
+    CVAE_REQUIRE(p != nullptr, CVAE_ECUDA, "fault flag unavailable");
+    int v = 0;
+    CVAE_CUDA(cudaMemcpyAsync(&v, p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CVAE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (v) {
+        int zero = 0;
+        CVAE_CUDA(cudaMemcpyAsync(p, &zero, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        CVAE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        cvae::set_error("device-side pipeline fault: a bounded mbarrier wait expired");
+        return CVAE_EDEVICE;
+    }
+    return CVAE_OK;
+}

@@ -13,9 +13,8 @@ namespace cvae {
 // ---------------------------------------------------------------------------------------------
 // Bounded waits.  A pipeline bug must never hang the GPU box: every mbarrier wait gives up after
 // kSpinLimit probes, raises a device-side flag and lets the kernel run to completion with garbage
-// results; the host wrapper turns the flag into CVAE_EDEVICE.
+// results; cvae_check_device_fault() turns the flag (a device int owned by api.cu) into CVAE_EDEVICE.
 // ---------------------------------------------------------------------------------------------
-__device__ int g_cvae_device_fault = 0;
 static constexpr uint32_t kSpinLimit = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -47,12 +46,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Returns false (and flags the fault) when the barrier never flips.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+// Returns false (and raises *fault) when the barrier never flips.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* fault) {
     for (uint32_t i = 0; i < kSpinLimit; ++i) {
         if (mbar_try_wait(bar, parity)) return true;
     }
-    atomicExch(&g_cvae_device_fault, 1);
+    atomicExch(fault, 1);
     return false;
 }
 

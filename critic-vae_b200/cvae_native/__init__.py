@@ -1,0 +1,2 @@
+"""Host-side binding of libcvae.so (the C ABI declared in include/cvae.h)."""
+from .binding import lib, check, CvaeError, ConvDesc, stream_ptr  # noqa: F401

@@ -1,0 +1,56 @@
+"""ctypes loader for libcvae.so.  There is NO fallback: a missing library is a hard error, because
+every result this package produces must come from the sm_100a kernels (BASELINE.json north_star)."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libcvae.so")
+
+
+class CvaeError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `make -C critic-vae_b200/csrc` (or __graft_entry__.build()). "
+        "There is no CPU or PyTorch fallback for the Critic-VAE hot path.")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+c_int, c_void_p, c_float, c_double, c_i64 = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_double, ctypes.c_int64
+
+
+class ConvDesc(ctypes.Structure):
+    """cvae_conv_desc (include/cvae.h)."""
+    _fields_ = [("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+                ("ksize", ctypes.c_int32), ("src_channels", ctypes.c_int32), ("n_total", ctypes.c_int32),
+                ("loader", ctypes.c_int32), ("epilogue", ctypes.c_int32), ("ktab", ctypes.c_int32),
+                ("tm", ctypes.c_int32),
+                ("src", c_void_p), ("src2", c_void_p), ("wpack", c_void_p), ("bias", c_void_p),
+                ("act", c_void_p), ("out", c_void_p), ("stats", c_void_p)]
+
+
+lib.cvae_last_error.restype = ctypes.c_char_p
+lib.cvae_version.restype = c_int
+lib.cvae_check_device_fault.argtypes = [c_void_p]
+lib.cvae_conv_gemm.argtypes = [ctypes.POINTER(ConvDesc), c_void_p]
+lib.cvae_conv_ksteps.argtypes = [c_int, c_int, c_int]
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise CvaeError(f"libcvae error {rc}: {lib.cvae_last_error().decode()}")
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# enums of include/cvae.h
+LOAD_NHWC, LOAD_NCHW3, LOAD_S2D, LOAD_S2D_NCHW3_DTANH = 0, 1, 2, 3
+EPI_STATS, EPI_BIAS_RELU, EPI_PHASE_BIAS_RELU, EPI_PHASE_BIAS_TANH, EPI_MASK, EPI_PLAIN = 0, 1, 2, 3, 4, 5
+KTAB_GENERIC, KTAB_PAIR8 = 0, 1

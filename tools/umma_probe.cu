@@ -5,6 +5,8 @@
 #include "../critic-vae_b200/csrc/umma.cuh"
 #include <stdio.h>
 
+__device__ int g_probe_fault = 0;
+
 using namespace cvae;
 
 struct ProbeArgs {
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
 
     if (tid == 0) {
         bool ok = true;
-        if (p.use_bulk) ok = mbar_wait(&bar_copy, 0);
+        if (p.use_bulk) ok = mbar_wait(&bar_copy, 0, &g_probe_fault);
         if (ok) {
             tc_fence_after();
             for (uint32_t k = 0; k < p.ksteps; ++k) {
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
         umma_commit(&bar_mma);
     }
     __syncwarp();
-    mbar_wait(&bar_mma, 0);
+    mbar_wait(&bar_mma, 0, &g_probe_fault);
     tc_fence_after();
 
     for (uint32_t c = 0; c < p.n; c += 8) {
@@ -98,7 +100,7 @@ extern "C" int probe_run(const void* a_img, uint32_t a_bytes, const void* b_img,
                                          (int)smem);
     if (e != cudaSuccess) return -1;
     int zero = 0;
-    cudaMemcpyToSymbol(g_cvae_device_fault, &zero, sizeof(int));
+    cudaMemcpyToSymbol(g_probe_fault, &zero, sizeof(int));
     probe_kernel<<<1, 128, smem>>>(p);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -106,6 +108,6 @@ extern "C" int probe_run(const void* a_img, uint32_t a_bytes, const void* b_img,
         return -2;
     }
     int fault = 0;
-    cudaMemcpyFromSymbol(&fault, g_cvae_device_fault, sizeof(int));
+    cudaMemcpyFromSymbol(&fault, g_probe_fault, sizeof(int));
     return fault ? -3 : 0;
 }
