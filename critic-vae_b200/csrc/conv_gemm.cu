@@ -14,6 +14,7 @@
 // and their autograd data-gradients.
 #include "common.cuh"
 #include "umma.cuh"
+#include "planes.cuh"
 
 namespace cvae {
 
@@ -31,9 +32,7 @@ struct ConvArgs {
     int plane_stride;    // bytes
     int ktab_mode;
     int nstages;
-    int src_c;           // channels of the raw source tensor (NHWC / S2D)
-    const void* src;
-    const void* src2;
+    PlaneSrc ps;         // where the A-operand planes come from
     const __nv_bfloat16* wpack;
     void* out;
     const float* bias;
@@ -43,78 +42,6 @@ struct ConvArgs {
 };
 
 static constexpr int kThreads = 192;  // warps 0-3: loader + epilogue, 4: weight producer, 5: MMA
-
-// --------------------------------------------------------------------------------------------
-// loaders: fill the halo planes for virtual pixels [v_first, v_first + L)
-// --------------------------------------------------------------------------------------------
-template <int LOADER>
-__device__ __forceinline__ void load_planes(const ConvArgs& a, uint8_t* planes, int v_first) {
-    for (int j = threadIdx.x; j < a.L; j += kThreads) {
-        const int v = v_first + j;
-        int vrow = v / a.PW;
-        int vcol = v - vrow * a.PW;
-        int n = vrow / a.IH;
-        int r = vrow - n * a.IH;
-        const bool valid = (v >= 0) && (vcol < a.W) && (r >= a.pad) && (n < a.B);
-        const int h = r - a.pad, w = vcol;
-        uint8_t* dst = planes + (size_t)j * 16;
-        if constexpr (LOADER == CVAE_LOAD_NHWC) {
-            const uint4* s = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const __nv_bfloat16*>(a.src) +
-                ((size_t)(n * a.H + h) * a.W + w) * a.src_c);
-            for (int q = 0; q < a.planes; ++q) {
-                uint4 val = valid ? __ldg(s + q) : make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(dst + (size_t)q * a.plane_stride) = val;
-            }
-        } else if constexpr (LOADER == CVAE_LOAD_S2D) {
-            // source [B][2H][2W][C]; plane q <-> (phase ab = q / (C/8), channel chunk q % (C/8))
-            const int cq = a.src_c >> 3;
-            for (int q = 0; q < a.planes; ++q) {
-                const int ab = q / cq, cc = q - ab * cq;
-                uint4 val = make_uint4(0, 0, 0, 0);
-                if (valid) {
-                    const size_t pix = ((size_t)(n * 2 * a.H + 2 * h + (ab >> 1)) * (2 * a.W) + 2 * w + (ab & 1));
-                    val = __ldg(reinterpret_cast<const uint4*>(
-                                    reinterpret_cast<const __nv_bfloat16*>(a.src) + pix * a.src_c) + cc);
-                }
-                *reinterpret_cast<uint4*>(dst + (size_t)q * a.plane_stride) = val;
-            }
-        } else if constexpr (LOADER == CVAE_LOAD_NCHW3) {
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (valid) {
-                const float* s = reinterpret_cast<const float*>(a.src) + ((size_t)n * 3 * a.H + h) * a.W + w;
-                const size_t cs = (size_t)a.H * a.W;
-                val.x = pack_bf16x2(__ldg(s), __ldg(s + cs));
-                val.y = pack_bf16x2(__ldg(s + 2 * cs), 0.f);
-            }
-            *reinterpret_cast<uint4*>(dst) = val;
-        } else {  // CVAE_LOAD_S2D_NCHW3_DTANH: 12 channels (a,b,c) + 4 zeros, two planes
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = 0.f;
-            if (valid) {
-                const int H2 = 2 * a.H, W2 = 2 * a.W;
-                const float* g = reinterpret_cast<const float*>(a.src);
-                const float* rc = reinterpret_cast<const float*>(a.src2);
-#pragma unroll
-                for (int ab = 0; ab < 4; ++ab)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const size_t idx = (((size_t)n * 3 + c) * H2 + 2 * h + (ab >> 1)) * W2 + 2 * w + (ab & 1);
-                        const float rv = __ldg(rc + idx);
-                        f[ab * 3 + c] = __ldg(g + idx) * (1.f - rv * rv);
-                    }
-            }
-            uint4 p0, p1;
-            p0.x = pack_bf16x2(f[0], f[1]);   p0.y = pack_bf16x2(f[2], f[3]);
-            p0.z = pack_bf16x2(f[4], f[5]);   p0.w = pack_bf16x2(f[6], f[7]);
-            p1.x = pack_bf16x2(f[8], f[9]);   p1.y = pack_bf16x2(f[10], f[11]);
-            p1.z = pack_bf16x2(f[12], f[13]); p1.w = pack_bf16x2(f[14], f[15]);
-            *reinterpret_cast<uint4*>(dst) = p0;
-            *reinterpret_cast<uint4*>(dst + a.plane_stride) = p1;
-        }
-    }
-}
 
 // --------------------------------------------------------------------------------------------
 // kernel
@@ -189,7 +116,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
 
     for (int chunk = blockIdx.x; chunk < a.num_chunks; chunk += gridDim.x) {
         const int v0 = a.pad * a.PW + chunk * a.tm * 128;  // first output pixel of this pass
-        load_planes<LOADER>(a, planes, v0 - a.halo);
+        fill_planes<LOADER>(a.ps, planes, a.plane_stride, v0 - a.halo, a.L, tid, kThreads);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -410,11 +337,12 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     a.ksteps = cvae_conv_ksteps(d->ksize, d->src_channels, d->ktab);
     a.ktab_mode = d->ktab;
     a.halo = a.pad * a.PW + a.pad;
-    a.src = d->src; a.src2 = d->src2; a.wpack = (const __nv_bfloat16*)d->wpack; a.out = d->out;
+    a.wpack = (const __nv_bfloat16*)d->wpack; a.out = d->out;
     a.bias = d->bias; a.act = (const __nv_bfloat16*)d->act; a.stats = d->stats;
     a.fault = fault_flag();
     CVAE_REQUIRE(a.fault != nullptr, CVAE_ECUDA, "conv_gemm: fault flag unavailable");
-    a.src_c = (d->loader == CVAE_LOAD_S2D) ? d->src_channels / 4 : d->src_channels;
+    a.ps = PlaneSrc{a.B, a.H, a.W, a.pad, a.PW, a.IH, a.planes,
+                    (d->loader == CVAE_LOAD_S2D) ? d->src_channels / 4 : d->src_channels, 0, d->src, d->src2};
 
     // K steps per weight stage: a whole tap when it fits in <= 16 KB, else 64 channels' worth
     if (d->ktab == CVAE_KTAB_PAIR8) a.ksps = 13;

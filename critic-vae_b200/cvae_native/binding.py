@@ -33,11 +33,23 @@ class ConvDesc(ctypes.Structure):
                 ("act", c_void_p), ("out", c_void_p), ("stats", c_void_p)]
 
 
+class WgradDesc(ctypes.Structure):
+    """cvae_wgrad_desc (include/cvae.h)."""
+    _fields_ = [("kind", ctypes.c_int32), ("batch", ctypes.c_int32), ("height", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("cout", ctypes.c_int32), ("cin", ctypes.c_int32),
+                ("splits", ctypes.c_int32),
+                ("x", c_void_p), ("dy", c_void_p), ("dy2", c_void_p), ("dw", c_void_p),
+                ("dbias", c_void_p), ("workspace", c_void_p)]
+
+
 lib.cvae_last_error.restype = ctypes.c_char_p
 lib.cvae_version.restype = c_int
 lib.cvae_check_device_fault.argtypes = [c_void_p]
 lib.cvae_conv_gemm.argtypes = [ctypes.POINTER(ConvDesc), c_void_p]
 lib.cvae_conv_ksteps.argtypes = [c_int, c_int, c_int]
+lib.cvae_conv_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(WgradDesc)]
+lib.cvae_conv_wgrad_workspace_bytes.restype = c_i64
+lib.cvae_conv_wgrad.argtypes = [ctypes.POINTER(WgradDesc), c_void_p]
 
 
 def check(rc: int) -> None:
@@ -54,3 +66,4 @@ def stream_ptr():
 LOAD_NHWC, LOAD_NCHW3, LOAD_S2D, LOAD_S2D_NCHW3_DTANH = 0, 1, 2, 3
 EPI_STATS, EPI_BIAS_RELU, EPI_PHASE_BIAS_RELU, EPI_PHASE_BIAS_TANH, EPI_MASK, EPI_PLAIN = 0, 1, 2, 3, 4, 5
 KTAB_GENERIC, KTAB_PAIR8 = 0, 1
+WGRAD_5X5, WGRAD_PHASE, WGRAD_SHIFT_FRAMES, WGRAD_SHIFT_PHASE12 = 0, 1, 2, 3

@@ -75,6 +75,31 @@ int cvae_conv_gemm(const cvae_conv_desc* d, void* stream);
  * nb = min(n_total, 128) */
 int cvae_conv_ksteps(int ksize, int src_channels, int ktab);
 
+/* ------------------------------------------------------------------------------------------------
+ * Convolution weight / bias gradients on tcgen05 (split-K over pixels, fp32 partials, fold to OIHW).
+ * Replaces autograd's dW, db of nn.Conv2d at vae_nets.py:69,74,79,84,117,121,125,129,133.
+ * ---------------------------------------------------------------------------------------------- */
+enum cvae_wgrad_kind {
+    CVAE_WGRAD_5X5 = 0,          /* x: bf16 NHWC [B][H][W][cin], dy: bf16 NHWC [B][H][W][cout]               */
+    CVAE_WGRAD_PHASE = 1,        /* up-sample-folded conv: x at [B][H][W][cin], dy at [B][2H][2W][cout]      */
+    CVAE_WGRAD_SHIFT_FRAMES = 2, /* encoder conv 0: x = fp32 NCHW frames [B][3][H][W], dy bf16 NHWC          */
+    CVAE_WGRAD_SHIFT_PHASE12 = 3 /* decoder conv 4: dy = fp32 NCHW d_recon [B][3][2H][2W], dy2 = recon       */
+};
+typedef struct {
+    int32_t kind, batch, height, width;
+    int32_t cout, cin;           /* reference weight shape [cout][cin][5][5] */
+    int32_t splits;              /* split-K factor, 0 = automatic */
+    const void* x;
+    const void* dy;
+    const void* dy2;
+    void* dw;                    /* fp32 [cout][cin][5][5], overwritten */
+    void* dbias;                 /* fp32 [cout], overwritten (may be NULL) */
+    void* workspace;             /* >= cvae_conv_wgrad_workspace_bytes(d) */
+} cvae_wgrad_desc;
+
+int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d);
+int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
