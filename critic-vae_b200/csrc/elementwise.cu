@@ -1,0 +1,320 @@
+// HBM-bound pieces around the conv GEMMs: BatchNorm finalize / apply+maxpool+activation forward and
+// backward, the fused latent kernel (reparameterise + critic concat, and its backward), Adam.
+// All are vectorised (16-byte) grid-stride kernels; reductions go warp-shuffle -> shared -> one
+// double atomic per channel per CTA.
+#include "common.cuh"
+
+namespace cvae {
+
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 unpack8(uint4 u) {
+    F8 f;
+    f.v[0] = bf16_lo(u.x); f.v[1] = bf16_hi(u.x); f.v[2] = bf16_lo(u.y); f.v[3] = bf16_hi(u.y);
+    f.v[4] = bf16_lo(u.z); f.v[5] = bf16_hi(u.z); f.v[6] = bf16_lo(u.w); f.v[7] = bf16_hi(u.w);
+    return f;
+}
+__device__ __forceinline__ uint4 pack8(const F8& f) {
+    return make_uint4(pack_bf16x2(f.v[0], f.v[1]), pack_bf16x2(f.v[2], f.v[3]),
+                      pack_bf16x2(f.v[4], f.v[5]), pack_bf16x2(f.v[6], f.v[7]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm finalize: nn.BatchNorm2d defaults (vae_nets.py:70,75,80,85).  ss = [scale|shift|mean|invstd]
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(int C, double count, int training, const double* stats,
+                                   const float* gamma, const float* beta, const float* conv_bias,
+                                   float* rmean, float* rvar, long long* nbt, float momentum, float eps,
+                                   float* ss) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mean, invstd;
+    if (training) {
+        // the conv ran WITHOUT its bias: a per-channel constant cancels in (x - mean); it only
+        // shows up in the running mean.
+        const double m = stats[c] / count;
+        double var = stats[C + c] / count - m * m;
+        if (var < 0) var = 0;
+        mean = (float)m;
+        invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const double unbiased = count > 1 ? var * count / (count - 1) : var;
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)(m + (double)conv_bias[c]);
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+        if (c == 0 && nbt) nbt[0] += 1;
+    } else {
+        mean = rmean[c] - conv_bias[c];
+        invstd = 1.f / sqrtf(rvar[c] + eps);
+    }
+    const float sc = gamma[c] * invstd;
+    ss[c] = sc;
+    ss[C + c] = beta[c] - mean * sc;
+    ss[2 * C + c] = mean;
+    ss[3 * C + c] = invstd;
+}
+
+__device__ __forceinline__ float act_fn(int act, float x) { return act == 0 ? fmaxf(x, 0.f) : tanhf(x); }
+
+// y = act(maxpool2x2(x*scale + shift)); x bf16 NHWC [B][H][W][C] -> y bf16 NHWC [B][H/2][W/2][C]
+__global__ void bn_pool_act_fwd_kernel(int B, int H, int W, int C, int act, const uint4* __restrict__ x,
+                                       const float* __restrict__ ss, uint4* __restrict__ y) {
+    const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const long long total = (long long)B * Ho * Wo * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cg);
+        long long p = i / cg;
+        const int wo = (int)(p % Wo); p /= Wo;
+        const int ho = (int)(p % Ho);
+        const int n = (int)(p / Ho);
+        const float4 s0 = __ldg((const float4*)(ss + c8 * 8)), s1 = __ldg((const float4*)(ss + c8 * 8 + 4));
+        const float4 h0 = __ldg((const float4*)(ss + C + c8 * 8)), h1 = __ldg((const float4*)(ss + C + c8 * 8 + 4));
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const size_t base = ((size_t)(n * H + 2 * ho) * W + 2 * wo) * cg + c8;
+        F8 m;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const F8 v = unpack8(__ldg(x + base + (size_t)(q >> 1) * W * cg + (size_t)(q & 1) * cg));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float b = fmaf(v.v[e], sc[e], sh[e]);
+                m.v[e] = q == 0 ? b : fmaxf(m.v[e], b);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m.v[e] = act_fn(act, m.v[e]);
+        y[i] = pack8(m);
+    }
+}
+
+// Backward of act(maxpool(bn(x))).  PASS 0: per-channel sum(g), sum(g*xhat) with g routed to the
+// arg-max position;  PASS 1: dx = gamma*invstd*(g_full - sum(g)/n - xhat*sum(g*xhat)/n) at all 4
+// positions, plus dgamma/dbeta.
+template <int PASS>
+__global__ void bn_pool_act_bwd_kernel(int B, int H, int W, int C, int act, const uint4* __restrict__ x,
+                                       const uint4* __restrict__ yact, const uint4* __restrict__ dy,
+                                       const float* __restrict__ ss, const float* __restrict__ gamma,
+                                       double* sums, uint4* __restrict__ dx, float* dgamma, float* dbeta) {
+    extern __shared__ float red[];  // PASS 0: [blockDim][16]
+    const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const int c8 = threadIdx.x % cg;
+    const int lanes = blockDim.x / cg;  // pixel lanes per block
+    const long long npix = (long long)B * Ho * Wo;
+    const double count = (double)B * H * W;
+    float sc[8], sh[8], mean[8], inv[8], k1[8], k2[8], gi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c8 * 8 + e;
+        sc[e] = ss[c]; sh[e] = ss[C + c]; mean[e] = ss[2 * C + c]; inv[e] = ss[3 * C + c];
+        if (PASS == 1) {
+            k1[e] = (float)(sums[c] / count);
+            k2[e] = (float)(sums[C + c] / count);
+            gi[e] = gamma[c] * inv[e];
+        }
+    }
+    float a1[8], a2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.f;
+
+    for (long long p = (long long)blockIdx.x * lanes + threadIdx.x / cg; p < npix; p += (long long)gridDim.x * lanes) {
+        const int wo = (int)(p % Wo);
+        const int ho = (int)((p / Wo) % Ho);
+        const int n = (int)(p / ((long long)Wo * Ho));
+        const size_t base = ((size_t)(n * H + 2 * ho) * W + 2 * wo) * cg + c8;
+        F8 xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xv[q] = unpack8(__ldg(x + base + (size_t)(q >> 1) * W * cg + (size_t)(q & 1) * cg));
+        const F8 yv = unpack8(__ldg(yact + p * cg + c8));
+        const F8 dv = unpack8(__ldg(dy + p * cg + c8));
+        F8 o[4];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int am = 0;
+            float best = fmaf(xv[0].v[e], sc[e], sh[e]);
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+                const float b = fmaf(xv[q].v[e], sc[e], sh[e]);
+                if (b > best) { best = b; am = q; }
+            }
+            const float g = dv.v[e] * (act == 0 ? (yv.v[e] > 0.f ? 1.f : 0.f) : (1.f - yv.v[e] * yv.v[e]));
+            if (PASS == 0) {
+                const float xh = ((am == 0 ? xv[0].v[e] : am == 1 ? xv[1].v[e] : am == 2 ? xv[2].v[e] : xv[3].v[e]) - mean[e]) * inv[e];
+                a1[e] += g;
+                a2[e] += g * xh;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float xh = (xv[q].v[e] - mean[e]) * inv[e];
+                    o[q].v[e] = gi[e] * ((q == am ? g : 0.f) - k1[e] - xh * k2[e]);
+                }
+            }
+        }
+        if (PASS == 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dx[base + (size_t)(q >> 1) * W * cg + (size_t)(q & 1) * cg] = pack8(o[q]);
+        }
+    }
+    if (PASS == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            red[threadIdx.x * 16 + e] = a1[e];
+            red[threadIdx.x * 16 + 8 + e] = a2[e];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < 2 * C; t += blockDim.x) {
+            const int which = t / C, c = t % C, g8 = c >> 3, e = c & 7;
+            float s = 0.f;
+            for (int l = 0; l < lanes; ++l) s += red[(l * cg + g8) * 16 + which * 8 + e];
+            atomicAdd(sums + which * C + c, (double)s);
+        }
+    } else if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            dbeta[c] = (float)sums[c];
+            dgamma[c] = (float)sums[C + c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Latent kernel (vae_nets.py:48-51 reparametrize, :143 critic concat) and its backward
+// ---------------------------------------------------------------------------------------------
+__global__ void latent_fwd_kernel(int B, int sample, const float* __restrict__ ml, const float* __restrict__ eps,
+                                  const float* __restrict__ pred, float* __restrict__ zc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 33) return;
+    const int b = i / 33, d = i - b * 33;
+    float v;
+    if (d == 32) v = pred[b];
+    else {
+        const float mu = ml[b * 64 + d];
+        v = sample ? fmaf(eps[b * 32 + d], expf(0.5f * ml[b * 64 + 32 + d]), mu) : mu;
+    }
+    zc[i] = v;
+}
+
+// d_ml[b][0:32] = dz + dmu_ext ; d_ml[b][32:64] = dz * eps * 0.5 * exp(0.5 logvar) + dlogvar_ext
+__global__ void latent_bwd_kernel(int B, const float* __restrict__ ml, const float* __restrict__ eps,
+                                  const float* __restrict__ dzc, const float* __restrict__ dmu_ext,
+                                  const float* __restrict__ dlv_ext, float* __restrict__ dml) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 32) return;
+    const int b = i >> 5, d = i & 31;
+    const float dz = dzc[b * 33 + d];
+    const float std_ = expf(0.5f * ml[b * 64 + 32 + d]);
+    dml[b * 64 + d] = dz + (dmu_ext ? dmu_ext[i] : 0.f);
+    dml[b * 64 + 32 + d] = dz * eps[i] * 0.5f * std_ + (dlv_ext ? dlv_ext[i] : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam defaults, vae.py:36): flat fp32 buffers, step counter on the device so the
+// launch is CUDA-graph replayable.  grad_scale folds the 1/world_size of the data-parallel mean.
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, const long long* __restrict__ step, float lr, float b1, float b2,
+                            float eps, float grad_scale) {
+    const double t = (double)(step[0] + 1);
+    const float bc1 = (float)(1.0 - pow((double)b1, t));
+    const float sq_bc2 = (float)sqrt(1.0 - pow((double)b2, t));
+    const float step_size = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gr = g[i] * grad_scale;
+        const float mi = m[i] + (1.f - b1) * (gr - m[i]);           // lerp form used by torch
+        const float vi = v[i] * b2 + (1.f - b2) * gr * gr;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / sq_bc2 + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
+}
+__global__ void adam_tick_kernel(long long* step) { step[0] += 1; }
+
+}  // namespace cvae
+
+using namespace cvae;
+
+static int grid_for(long long items, int threads, int per_sm = 8) {
+    long long b = (items + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+extern "C" int cvae_bn_finalize(int channels, int64_t count, int training, const double* stats,
+                                const float* gamma, const float* beta, const float* conv_bias,
+                                float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                float momentum, float eps, float* scale_shift, void* stream) {
+    CVAE_REQUIRE(channels > 0 && count > 0, CVAE_EINVAL, "bn_finalize: empty");
+    CVAE_REQUIRE(gamma && beta && conv_bias && running_mean && running_var && scale_shift, CVAE_EINVAL, "bn_finalize: null tensor");
+    CVAE_REQUIRE(!training || stats, CVAE_EINVAL, "bn_finalize: training needs stats");
+    bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        channels, (double)count, training, stats, gamma, beta, conv_bias, running_mean, running_var,
+        (long long*)num_batches_tracked, momentum, eps, scale_shift);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_bn_pool_act_fwd(int batch, int height, int width, int channels, int act,
+                                    const void* conv_out, const float* scale_shift, void* out, void* stream) {
+    CVAE_REQUIRE(batch > 0 && height % 2 == 0 && width % 2 == 0 && channels % 8 == 0, CVAE_EINVAL, "bn_pool_act_fwd: shape");
+    CVAE_REQUIRE(conv_out && scale_shift && out, CVAE_EINVAL, "bn_pool_act_fwd: null tensor");
+    const long long items = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
+    bn_pool_act_fwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+        batch, height, width, channels, act, (const uint4*)conv_out, scale_shift, (uint4*)out);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_bn_pool_act_bwd(int batch, int height, int width, int channels, int act,
+                                    const void* conv_out, const void* act_out, const void* d_act,
+                                    const float* scale_shift, const float* gamma, double* sums,
+                                    void* d_conv, float* dgamma, float* dbeta, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVAE_REQUIRE(batch > 0 && height % 2 == 0 && width % 2 == 0 && channels % 8 == 0 && channels <= 256 &&
+                     256 % (channels / 8) == 0, CVAE_EINVAL, "bn_pool_act_bwd: shape");
+    CVAE_REQUIRE(conv_out && act_out && d_act && scale_shift && gamma && sums && d_conv && dgamma && dbeta,
+                 CVAE_EINVAL, "bn_pool_act_bwd: null tensor");
+    CVAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * channels, stream));
+    const int threads = 256, lanes = threads / (channels / 8);
+    const long long npix = (long long)batch * (height / 2) * (width / 2);
+    long long blocks = (npix + lanes - 1) / lanes;
+    const long long cap = (long long)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    bn_pool_act_bwd_kernel<0><<<(int)blocks, threads, threads * 16 * sizeof(float), stream>>>(
+        batch, height, width, channels, act, (const uint4*)conv_out, (const uint4*)act_out, (const uint4*)d_act,
+        scale_shift, gamma, sums, nullptr, nullptr, nullptr);
+    CVAE_LAUNCH_CHECK();
+    bn_pool_act_bwd_kernel<1><<<(int)blocks, threads, 0, stream>>>(
+        batch, height, width, channels, act, (const uint4*)conv_out, (const uint4*)act_out, (const uint4*)d_act,
+        scale_shift, gamma, sums, (uint4*)d_conv, dgamma, dbeta);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_latent_fwd(int batch, int sample, const float* mu_logvar, const float* eps,
+                               const float* pred, float* z_pred, void* stream) {
+    CVAE_REQUIRE(batch > 0 && mu_logvar && pred && z_pred && (!sample || eps), CVAE_EINVAL, "latent_fwd: bad argument");
+    latent_fwd_kernel<<<(batch * 33 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(batch, sample, mu_logvar, eps, pred, z_pred);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_latent_bwd(int batch, const float* mu_logvar, const float* eps, const float* d_z_pred,
+                               const float* dmu_ext, const float* dlogvar_ext, float* d_mu_logvar, void* stream) {
+    CVAE_REQUIRE(batch > 0 && mu_logvar && eps && d_z_pred && d_mu_logvar, CVAE_EINVAL, "latent_bwd: bad argument");
+    latent_bwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(batch, mu_logvar, eps, d_z_pred, dmu_ext,
+                                                                                 dlogvar_ext, d_mu_logvar);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                              int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale,
+                              void* stream) {
+    CVAE_REQUIRE(n > 0 && params && grads && exp_avg && exp_avg_sq && step, CVAE_EINVAL, "adam_step: bad argument");
+    adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq,
+                                                                    (const long long*)step, lr, beta1, beta2, eps, grad_scale);
+    CVAE_LAUNCH_CHECK();
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)step);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}

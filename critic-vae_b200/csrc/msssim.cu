@@ -1,0 +1,332 @@
+// Reconstruction + KL loss (vae_nets.py:53-62): 5-level MS-SSIM (vae_nets.py:150-247) forward and
+// backward, KLD (vae_nets.py:57-58).
+//
+// One CTA per (frame, channel) plane keeps both image pyramids in shared memory and runs the 11x11
+// window as two separable 11-tap passes (the reference window is an outer product, vae_nets.py:175-179)
+// with 8 outputs per thread per pass so the FP32 pipe, not shared-memory bandwidth, is the limiter.
+// The MS-SSIM means are batch-global (vae_nets.py:207,212) and enter the loss non-linearly
+// (vae_nets.py:243-246), hence two phases: forward accumulates the ten level sums with double
+// atomics, loss_finalize turns them into the loss and the per-level chain-rule coefficients, and
+// the backward kernel recomputes the maps and applies them.  powf of a negative cs mean gives NaN
+// exactly like the reference's `mcs ** weights`.
+#include "common.cuh"
+
+namespace cvae {
+
+struct Window { float g[11]; };
+
+static constexpr int kLevels = 5;
+// padded strides (S+1) keep both the row-wise and the column-wise pass bank-conflict free
+__host__ __device__ constexpr int lvl_size(int l) { return 64 >> l; }
+__host__ __device__ constexpr int lvl_off(int l) {
+    int o = 0;
+    for (int i = 0; i < l; ++i) o += lvl_size(i) * (lvl_size(i) + 1);
+    return o;
+}
+static constexpr int kPyr = lvl_off(5);          // 5580 floats
+static constexpr int kMap = 64 * 65;             // one padded 64x64 map
+static constexpr int kMsThreads = 256;
+
+// horizontal 11-tap pass producing NM maps from per-pixel inputs built by `make`.
+// task t -> (row = t % S, segment of 8 columns = t / S)
+template <int NM, typename Make>
+__device__ __forceinline__ void hpass(int S, const Window& w, float* __restrict__ out, Make make) {
+    const int st = S + 1, nseg = (S + 7) >> 3;
+    for (int t = threadIdx.x; t < S * nseg; t += kMsThreads) {
+        const int r = t % S, c0 = (t / S) * 8;
+        float acc[NM][8];
+#pragma unroll
+        for (int m = 0; m < NM; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[m][j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+            const int c = c0 - 5 + i;
+            float v[NM];
+            if (c >= 0 && c < S) make(r * st + c, v);
+            else {
+#pragma unroll
+                for (int m = 0; m < NM; ++m) v[m] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = i - j;  // tap index: input c = (c0+j) - 5 + k
+                if (k >= 0 && k < 11) {
+#pragma unroll
+                    for (int m = 0; m < NM; ++m) acc[m][j] = fmaf(w.g[k], v[m], acc[m][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < S) {
+#pragma unroll
+                for (int m = 0; m < NM; ++m) out[m * kMap + r * st + c0 + j] = acc[m][j];
+            }
+    }
+}
+
+// vertical 11-tap pass over NM maps; `sink(idx, vals)` consumes the blurred values of pixel idx.
+template <int NM, typename Sink>
+__device__ __forceinline__ void vpass(int S, const Window& w, const float* __restrict__ in, Sink sink) {
+    const int st = S + 1, nseg = (S + 7) >> 3;
+    for (int t = threadIdx.x; t < S * nseg; t += kMsThreads) {
+        const int c = t % S, r0 = (t / S) * 8;
+        float acc[NM][8];
+#pragma unroll
+        for (int m = 0; m < NM; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[m][j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+            const int r = r0 - 5 + i;
+            if (r >= 0 && r < S) {
+#pragma unroll
+                for (int m = 0; m < NM; ++m) {
+                    const float v = in[m * kMap + r * st + c];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = i - j;
+                        if (k >= 0 && k < 11) acc[m][j] = fmaf(w.g[k], v, acc[m][j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (r0 + j < S) {
+                float v[NM];
+#pragma unroll
+                for (int m = 0; m < NM; ++m) v[m] = acc[m][j];
+                sink((r0 + j) * st + c, v);
+            }
+    }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (kMsThreads >> 5) ? scratch[threadIdx.x] : 0.f;
+        s = warp_sum(s);
+    }
+    return s;  // valid in warp 0
+}
+
+// coef layout (floats): [0..3] dL/d(cs_map pixel) for levels 0..3, [4] dL/d(ssim_map pixel) level 4
+template <bool BWD>
+__global__ void __launch_bounds__(kMsThreads, 1)
+msssim_kernel(int planes, const float* __restrict__ recon, const float* __restrict__ x, const Window w,
+              double* __restrict__ sums, const float* __restrict__ coef, const float* __restrict__ grad_out,
+              float* __restrict__ d_recon) {
+    extern __shared__ float sm[];
+    float* A = sm;                    // recon pyramid
+    float* Bp = A + kPyr;             // target pyramid
+    float* Hm = Bp + kPyr;            // 5 horizontally blurred maps (reused for the 3 gradient maps)
+    float* Dm = Hm + 5 * kMap;        // BWD: 3 derivative maps
+    float* G = Dm + (BWD ? 3 * kMap : 0);  // BWD: per-level gradient pyramid
+    __shared__ float scratch[8];
+    const float C1 = 0.0001f, C2 = 0.0009f;
+
+    for (int plane = blockIdx.x; plane < planes; plane += gridDim.x) {
+        const float* ra = recon + (size_t)plane * 4096;
+        const float* xb = x + (size_t)plane * 4096;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4096; i += kMsThreads) {
+            const int r = i >> 6, c = i & 63;
+            A[r * 65 + c] = __ldg(ra + i);
+            Bp[r * 65 + c] = __ldg(xb + i);
+        }
+        __syncthreads();
+        for (int l = 1; l < kLevels; ++l) {   // F.avg_pool2d(., (2,2)) pyramid, vae_nets.py:232-233
+            const int S = lvl_size(l), st = S + 1, ps = 2 * S + 1;
+            const float* pa = A + lvl_off(l - 1);
+            const float* pb = Bp + lvl_off(l - 1);
+            for (int i = threadIdx.x; i < S * S; i += kMsThreads) {
+                const int r = i / S, c = i % S;
+                const int q = 2 * r * ps + 2 * c;
+                A[lvl_off(l) + r * st + c] = 0.25f * (pa[q] + pa[q + 1] + pa[q + ps] + pa[q + ps + 1]);
+                Bp[lvl_off(l) + r * st + c] = 0.25f * (pb[q] + pb[q + 1] + pb[q + ps] + pb[q + ps + 1]);
+            }
+            __syncthreads();
+        }
+
+        for (int l = 0; l < kLevels; ++l) {
+            const int S = lvl_size(l);
+            const float* a = A + lvl_off(l);
+            const float* b = Bp + lvl_off(l);
+            hpass<5>(S, w, Hm, [&](int idx, float* v) {
+                const float av = a[idx], bv = b[idx];
+                v[0] = av; v[1] = bv; v[2] = av * av; v[3] = bv * bv; v[4] = av * bv;
+            });
+            __syncthreads();
+            float cs_acc = 0.f, ss_acc = 0.f;
+            const float gc = BWD ? coef[l < 4 ? l : 4] : 0.f;
+            vpass<5>(S, w, Hm, [&](int idx, const float* v) {
+                const float mu1 = v[0], mu2 = v[1];
+                const float s1 = v[2] - mu1 * mu1, s2 = v[3] - mu2 * mu2, s12 = v[4] - mu1 * mu2;
+                const float v1 = 2.f * s12 + C2, v2 = s1 + s2 + C2;
+                const float a1 = 2.f * mu1 * mu2 + C1, a2 = mu1 * mu1 + mu2 * mu2 + C1;
+                const float cs = v1 / v2;
+                cs_acc += cs;
+                ss_acc += (a1 * v1) / (a2 * v2);
+                if (BWD) {
+                    // derivative of the level's scalar w.r.t. mu1, blur(a*a), blur(a*b) at this pixel
+                    float dmu, daa, dab;
+                    if (l < 4) {           // cs = v1 / v2
+                        dab = 2.f / v2;
+                        daa = -v1 / (v2 * v2);
+                        dmu = (-2.f * mu2) / v2 + (v1 / (v2 * v2)) * (2.f * mu1);
+                    } else {               // ssim = (a1 v1) / (a2 v2)
+                        const float den = a2 * v2, Sv = (a1 * v1) / den;
+                        const float dv1 = a1 / den, dv2 = -Sv / v2, da1 = v1 / den, da2 = -Sv / a2;
+                        dab = 2.f * dv1;
+                        daa = dv2;
+                        dmu = dv1 * (-2.f * mu2) + dv2 * (-2.f * mu1) + da1 * (2.f * mu2) + da2 * (2.f * mu1);
+                    }
+                    Dm[idx] = dmu * gc;
+                    Dm[kMap + idx] = daa * gc;
+                    Dm[2 * kMap + idx] = dab * gc;
+                }
+            });
+            if (!BWD) {
+                const float cs_tot = block_sum(cs_acc, scratch);
+                const float ss_tot = block_sum(ss_acc, scratch);
+                if (threadIdx.x == 0) {
+                    atomicAdd(sums + l, (double)cs_tot);
+                    atomicAdd(sums + 5 + l, (double)ss_tot);
+                }
+            }
+            __syncthreads();
+            if (BWD) {
+                // dL/da_l(q) = blur(dmu)(q) + 2 a(q) blur(daa)(q) + b(q) blur(dab)(q)   (symmetric window)
+                hpass<3>(S, w, Hm, [&](int idx, float* v) {
+                    v[0] = Dm[idx]; v[1] = Dm[kMap + idx]; v[2] = Dm[2 * kMap + idx];
+                });
+                __syncthreads();
+                float* g = G + lvl_off(l);
+                vpass<3>(S, w, Hm, [&](int idx, const float* v) {
+                    g[idx] = v[0] + 2.f * a[idx] * v[1] + b[idx] * v[2];
+                });
+                __syncthreads();
+            }
+        }
+
+        if (BWD) {
+            // chain through the average pools: each finer pixel inherits 1/4 of its parent's gradient
+            const float go = grad_out ? __ldg(grad_out) : 1.f;
+            float* dr = d_recon + (size_t)plane * 4096;
+            for (int i = threadIdx.x; i < 4096; i += kMsThreads) {
+                const int r = i >> 6, c = i & 63;
+                float acc = 0.f, scale = 1.f;
+#pragma unroll
+                for (int l = 0; l < kLevels; ++l) {
+                    const int S = lvl_size(l);
+                    acc += scale * G[lvl_off(l) + (r >> l) * (S + 1) + (c >> l)];
+                    scale *= 0.25f;
+                }
+                dr[i] = acc * go;
+            }
+        }
+    }
+}
+
+// one block: KLD reduction + loss scalars + chain-rule coefficients
+__global__ void loss_finalize_kernel(int B, const float* __restrict__ ml, const double* __restrict__ sums,
+                                     float kld_weight, float* __restrict__ losses, float* __restrict__ coef) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
+        const int b = i >> 5, d = i & 31;
+        const float mu = ml[b * 64 + d], lv = ml[b * 64 + 32 + d];
+        acc += (double)(1.f + lv - mu * mu - expf(lv));
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+        const float kld = (float)(-0.5 * tot / B) * kld_weight;
+        const float wts[5] = {0.0448f, 0.2856f, 0.3001f, 0.2363f, 0.1333f};
+        float cs[5], ss4, P = 1.f;
+        for (int l = 0; l < 5; ++l) cs[l] = (float)(sums[l] / ((double)B * 3 * lvl_size(l) * lvl_size(l)));
+        ss4 = (float)(sums[9] / ((double)B * 3 * 16));
+        const float p4 = powf(ss4, wts[4]);
+        for (int l = 0; l < 4; ++l) P *= powf(cs[l], wts[l]) * p4;   // torch.prod(pow1[:-1] * pow2[-1])
+        const float recon_loss = 1.f - P;
+        losses[0] = recon_loss + kld;
+        losses[1] = recon_loss;
+        losses[2] = kld;
+        // L = 1 - P;  dL/dcs_l = -P w_l / cs_l;  dL/dss4 = -P 4 w_4 / ss4;  per-pixel: / N_l
+        for (int l = 0; l < 4; ++l)
+            coef[l] = (-P * wts[l] / cs[l]) / ((float)B * 3.f * lvl_size(l) * lvl_size(l));
+        coef[4] = (-P * 4.f * wts[4] / ss4) / ((float)B * 3.f * 16.f);
+    }
+}
+
+// dKLD/dmu = w mu / B, dKLD/dlogvar = w 0.5 (exp(lv) - 1) / B, times the upstream gradient
+__global__ void kld_bwd_kernel(int B, const float* __restrict__ ml, float kld_weight, const float* __restrict__ grad_out,
+                               float* __restrict__ dmu, float* __restrict__ dlv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 32) return;
+    const int b = i >> 5, d = i & 31;
+    const float go = (grad_out ? __ldg(grad_out) : 1.f) * kld_weight / (float)B;
+    dmu[i] = go * ml[b * 64 + d];
+    dlv[i] = go * 0.5f * (expf(ml[b * 64 + 32 + d]) - 1.f);
+}
+
+}  // namespace cvae
+
+using namespace cvae;
+
+static size_t ms_smem(bool bwd) {
+    return sizeof(float) * (size_t)(2 * kPyr + 5 * kMap + (bwd ? 3 * kMap + kPyr : 0));
+}
+
+extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar,
+                             const float* window11, float kld_weight, double* sums, float* coef, float* losses,
+                             void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVAE_REQUIRE(batch > 0 && recon && x && mu_logvar && window11 && sums && coef && losses, CVAE_EINVAL, "loss_fwd: bad argument");
+    Window w;
+    memcpy(w.g, window11, sizeof(w.g));
+    static thread_local bool configured = false;
+    if (!configured) {
+        CVAE_CUDA(cudaFuncSetAttribute(msssim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms_smem(false)));
+        configured = true;
+    }
+    CVAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 10, stream));
+    const int planes = batch * 3;
+    const int grid = planes < sm_count() ? planes : sm_count();
+    msssim_kernel<false><<<grid, kMsThreads, ms_smem(false), stream>>>(planes, recon, x, w, sums, nullptr, nullptr, nullptr);
+    CVAE_LAUNCH_CHECK();
+    loss_finalize_kernel<<<1, 1024, 0, stream>>>(batch, mu_logvar, sums, kld_weight, losses, coef);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_loss_bwd(int batch, const float* recon, const float* x, const float* mu_logvar,
+                             const float* window11, float kld_weight, const float* coef, const float* grad_out,
+                             float* d_recon, float* d_mu, float* d_logvar, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVAE_REQUIRE(batch > 0 && recon && x && mu_logvar && window11 && coef && d_recon && d_mu && d_logvar, CVAE_EINVAL,
+                 "loss_bwd: bad argument");
+    Window w;
+    memcpy(w.g, window11, sizeof(w.g));
+    static thread_local bool configured = false;
+    if (!configured) {
+        CVAE_CUDA(cudaFuncSetAttribute(msssim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms_smem(true)));
+        configured = true;
+    }
+    const int planes = batch * 3;
+    const int grid = planes < sm_count() ? planes : sm_count();
+    msssim_kernel<true><<<grid, kMsThreads, ms_smem(true), stream>>>(planes, recon, x, w, nullptr, coef, grad_out, d_recon);
+    CVAE_LAUNCH_CHECK();
+    kld_bwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, stream>>>(batch, mu_logvar, kld_weight, grad_out, d_mu, d_logvar);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}

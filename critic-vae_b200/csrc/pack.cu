@@ -1,0 +1,137 @@
+// Weight packing: fp32 master weights (reference layouts: OIHW conv, [out][in] linear) -> the bf16
+// UMMA core-matrix blocks conv_gemm.cu streams (forward, data-gradient and up-sample-folded "phase"
+// variants) and the transposed / NHWC-permuted fp32 matrices of the three Linear layers.
+// One launch packs every layer; it runs at the head of each forward so Adam updates, load_state_dict
+// or any user edit of a parameter are always picked up.
+#include "common.cuh"
+
+namespace cvae {
+
+struct PackJobs {
+    int count;
+    long long total;
+    cvae_pack_job job[CVAE_MAX_PACK_JOBS];
+    long long start[CVAE_MAX_PACK_JOBS + 1];
+};
+
+// 5x5 taps (ky range lo..hi) folded onto low-res tap t (0..2) for output phase a:
+// conv5x5(upsample2(x))[2i+a] reads x[(2i+a+ky-2)>>1]
+__device__ __forceinline__ void phase_range(int a, int t, int& lo, int& hi) {
+    if (a == 0) { lo = t == 0 ? 0 : (t == 1 ? 2 : 4); hi = t == 0 ? 1 : (t == 1 ? 3 : 4); }
+    else        { lo = t == 0 ? 0 : (t == 1 ? 1 : 3); hi = t == 0 ? 0 : (t == 1 ? 2 : 4); }
+}
+
+// effective 3x3 weight of phase (a,b) for (co, ci, ty, tx): fp32 sum in ky-major order
+__device__ __forceinline__ float phase_weight(const float* W, int cin, int co, int ci, int a, int b, int ty, int tx) {
+    int y0, y1, x0, x1;
+    phase_range(a, ty, y0, y1);
+    phase_range(b, tx, x0, x1);
+    float acc = 0.f;
+    for (int ky = y0; ky <= y1; ++ky)
+        for (int kx = x0; kx <= x1; ++kx) acc = acc + W[((size_t)co * cin + ci) * 25 + ky * 5 + kx];
+    return acc;
+}
+
+__device__ float pack_value(const cvae_pack_job& j, long long i, bool& is_bf16) {
+    const float* W = (const float*)j.src;
+    is_bf16 = true;
+    if (j.kind == CVAE_PACK_FC) {         // dst fp32 [4096 k'][64]: k' = p*256 + c  <->  k = c*16 + p
+        is_bf16 = false;
+        const int jj = (int)(i % 64), kp = (int)(i / 64);
+        const int k = (kp % 256) * 16 + kp / 256;
+        return jj < 32 ? W[(size_t)jj * 4096 + k] : ((const float*)j.src2)[(size_t)(jj - 32) * 4096 + k];
+    }
+    if (j.kind == CVAE_PACK_DECIN) {      // dst fp32 [34][4096 k']: rows 0..32 = W^T, row 33 = bias
+        is_bf16 = false;
+        const int kp = (int)(i % 4096), r = (int)(i / 4096);
+        const int k = (kp % 256) * 16 + kp / 256;
+        return r < 33 ? W[(size_t)k * 33 + r] : ((const float*)j.src2)[k];
+    }
+    // UMMA K-major blocks: [nb][kstep][n/8][kchunk 2][row 8][elem 8]
+    const int N = j.n, NB = N < 128 ? N : 128;
+    const int e = (int)(i & 7), r = (int)((i >> 3) & 7), kc = (int)((i >> 6) & 1);
+    const int ng = (int)((i >> 7) % (NB / 8));
+    const long long rest = i / (16LL * NB);
+    const int ks = (int)(rest % j.ksteps), nb = (int)(rest / j.ksteps);
+    const int n = nb * NB + ng * 8 + r, k16 = kc * 8 + e;
+
+    if (j.kind == CVAE_PACK_PAIR8) {      // encoder conv 0: two taps of an 8-channel padded pixel per K step
+        const int c = k16 & 7, half = k16 >> 3;
+        if (c >= 3) return 0.f;
+        int ky, kx;
+        if (ks < 10) { ky = ks >> 1; kx = (ks & 1) * 2 + half; }
+        else if (ks < 12) { ky = (ks - 10) * 2 + half; kx = 4; }
+        else { if (half) return 0.f; ky = 4; kx = 4; }
+        return W[((size_t)n * 3 + c) * 25 + ky * 5 + kx];
+    }
+    const int cpt = j.k_channels / 16;  // K steps per tap
+    const int tap = ks / cpt, c = (ks % cpt) * 16 + k16;
+    switch (j.kind) {
+        case CVAE_PACK_FWD5:     // n = co, c = ci
+            return W[((size_t)n * j.cin + c) * 25 + tap];
+        case CVAE_PACK_DGRAD5:   // n = ci, c = co, flipped taps
+            return W[((size_t)c * j.cin + n) * 25 + (24 - tap)];
+        case CVAE_PACK_PHASE_FWD: {  // n = (ab, co), c = ci, 3x3 taps
+            if (n >= 4 * j.cout) return 0.f;
+            const int ab = n / j.cout, co = n % j.cout;
+            return phase_weight(W, j.cin, co, c, ab >> 1, ab & 1, tap / 3, tap % 3);
+        }
+        case CVAE_PACK_PHASE_DGRAD: {  // n = ci, c = (ab, co), flipped 3x3 taps
+            if (c >= 4 * j.cout) return 0.f;
+            const int ab = c / j.cout, co = c % j.cout, ft = 8 - tap;
+            return phase_weight(W, j.cin, co, n, ab >> 1, ab & 1, ft / 3, ft % 3);
+        }
+    }
+    return 0.f;
+}
+
+__global__ void pack_weights_kernel(const PackJobs jobs) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < jobs.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = jobs.count - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs.start[mid] <= idx) lo = mid; else hi = mid - 1;
+        }
+        const cvae_pack_job& j = jobs.job[lo];
+        const long long i = idx - jobs.start[lo];
+        bool is_bf16;
+        const float v = pack_value(j, i, is_bf16);
+        if (is_bf16) ((__nv_bfloat16*)j.dst)[i] = __float2bfloat16_rn(v);
+        else ((float*)j.dst)[i] = v;
+    }
+}
+
+}  // namespace cvae
+
+using namespace cvae;
+
+extern "C" int64_t cvae_pack_elems(const cvae_pack_job* j) {
+    if (!j) return -1;
+    if (j->kind == CVAE_PACK_FC) return 4096LL * 64;
+    if (j->kind == CVAE_PACK_DECIN) return 34LL * 4096;
+    return (int64_t)j->n * j->ksteps * 16;
+}
+
+extern "C" int cvae_pack_weights(const cvae_pack_job* jobs, int count, void* stream) {
+    CVAE_REQUIRE(jobs && count > 0 && count <= CVAE_MAX_PACK_JOBS, CVAE_EINVAL, "pack_weights: %d jobs", count);
+    PackJobs pj{};
+    pj.count = count;
+    long long total = 0;
+    for (int i = 0; i < count; ++i) {
+        CVAE_REQUIRE(jobs[i].src && jobs[i].dst, CVAE_EINVAL, "pack_weights: job %d has a null tensor", i);
+        if (jobs[i].kind != CVAE_PACK_FC && jobs[i].kind != CVAE_PACK_DECIN)
+            CVAE_REQUIRE(jobs[i].n % 16 == 0 && jobs[i].ksteps > 0, CVAE_EINVAL, "pack_weights: job %d shape", i);
+        pj.job[i] = jobs[i];
+        pj.start[i] = total;
+        total += cvae_pack_elems(&jobs[i]);
+    }
+    pj.start[count] = total;
+    pj.total = total;
+    const int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_weights_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(pj);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}

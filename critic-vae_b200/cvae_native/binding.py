@@ -52,6 +52,42 @@ lib.cvae_conv_wgrad_workspace_bytes.restype = c_i64
 lib.cvae_conv_wgrad.argtypes = [ctypes.POINTER(WgradDesc), c_void_p]
 
 
+class PackJob(ctypes.Structure):
+    """cvae_pack_job (include/cvae.h)."""
+    _fields_ = [("kind", ctypes.c_int32), ("n", ctypes.c_int32), ("ksteps", ctypes.c_int32),
+                ("k_channels", ctypes.c_int32), ("cout", ctypes.c_int32), ("cin", ctypes.c_int32),
+                ("src", c_void_p), ("src2", c_void_p), ("dst", c_void_p)]
+
+
+P = c_void_p
+_SIGS = {
+    "cvae_pack_elems": ([ctypes.POINTER(PackJob)], c_i64),
+    "cvae_pack_weights": ([ctypes.POINTER(PackJob), c_int, P], c_int),
+    "cvae_bn_finalize": ([c_int, c_i64, c_int, P, P, P, P, P, P, P, c_float, c_float, P, P], c_int),
+    "cvae_bn_pool_act_fwd": ([c_int, c_int, c_int, c_int, c_int, P, P, P, P], c_int),
+    "cvae_bn_pool_act_bwd": ([c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P], c_int),
+    "cvae_fc_fwd": ([c_int, P, P, P, P, P, P], c_int),
+    "cvae_fc_bwd": ([c_int, P, P, P, P, P, P, P, P, P], c_int),
+    "cvae_decin_fwd": ([c_int, P, P, P, P], c_int),
+    "cvae_decin_bwd": ([c_int, P, P, P, P, P, P, P], c_int),
+    "cvae_latent_fwd": ([c_int, c_int, P, P, P, P, P], c_int),
+    "cvae_latent_bwd": ([c_int, P, P, P, P, P, P, P], c_int),
+    "cvae_loss_fwd": ([c_int, P, P, P, ctypes.POINTER(c_float), c_float, P, P, P, P], c_int),
+    "cvae_loss_bwd": ([c_int, P, P, P, ctypes.POINTER(c_float), c_float, P, P, P, P, P, P], c_int),
+    "cvae_adam_step": ([c_i64, P, P, P, P, P, c_float, c_float, c_float, c_float, c_float, P], c_int),
+    "cvae_critic_param_count": ([], c_int),
+    "cvae_critic_fwd": ([c_int, P, P, P, P], c_int),
+    "cvae_diff_grey": ([c_int, P, P, P, P, P], c_int),
+    "cvae_mask_iou": ([c_int, P, P, c_double, c_double, c_int, c_int, P, P, P, P, P, P], c_int),
+}
+for _name, (_args, _res) in _SIGS.items():
+    getattr(lib, _name).argtypes = _args
+    getattr(lib, _name).restype = _res
+
+EXPORTS = ["cvae_last_error", "cvae_version", "cvae_check_device_fault", "cvae_conv_gemm", "cvae_conv_ksteps",
+           "cvae_conv_wgrad_workspace_bytes", "cvae_conv_wgrad"] + list(_SIGS)
+
+
 def check(rc: int) -> None:
     if rc != 0:
         raise CvaeError(f"libcvae error {rc}: {lib.cvae_last_error().decode()}")
@@ -67,3 +103,5 @@ LOAD_NHWC, LOAD_NCHW3, LOAD_S2D, LOAD_S2D_NCHW3_DTANH = 0, 1, 2, 3
 EPI_STATS, EPI_BIAS_RELU, EPI_PHASE_BIAS_RELU, EPI_PHASE_BIAS_TANH, EPI_MASK, EPI_PLAIN = 0, 1, 2, 3, 4, 5
 KTAB_GENERIC, KTAB_PAIR8 = 0, 1
 WGRAD_5X5, WGRAD_PHASE, WGRAD_SHIFT_FRAMES, WGRAD_SHIFT_PHASE12 = 0, 1, 2, 3
+PACK_FWD5, PACK_DGRAD5, PACK_PAIR8, PACK_PHASE_FWD, PACK_PHASE_DGRAD, PACK_FC, PACK_DECIN = range(7)
+ACT_RELU, ACT_TANH = 0, 1

@@ -100,6 +100,111 @@ typedef struct {
 int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d);
 int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Weight packing (fp32 master parameters in the reference's layouts -> kernel operand layouts).
+ * One launch for all layers; no reference counterpart (cuDNN/MKL-DNN pack internally).
+ * ---------------------------------------------------------------------------------------------- */
+#define CVAE_MAX_PACK_JOBS 24
+enum cvae_pack_kind {
+    CVAE_PACK_FWD5 = 0,        /* conv forward: n = cout, k_channels = cin, 25 taps                  */
+    CVAE_PACK_DGRAD5 = 1,      /* conv data-gradient: n = cin, k_channels = cout, flipped taps       */
+    CVAE_PACK_PAIR8 = 2,       /* encoder conv 0 (3 -> 32), 13 K steps of two taps                   */
+    CVAE_PACK_PHASE_FWD = 3,   /* conv on 2x up-sampled input as 3x3 conv with n = 4*cout (padded)   */
+    CVAE_PACK_PHASE_DGRAD = 4, /* its data-gradient: n = cin, k_channels = 4*cout (padded to 16)     */
+    CVAE_PACK_FC = 5,          /* src = fc_mu.weight, src2 = fc_var.weight -> fp32 [4096 nhwc][64]    */
+    CVAE_PACK_DECIN = 6        /* src = decoder_input.weight, src2 = bias -> fp32 [34][4096 nhwc]     */
+};
+typedef struct {
+    int32_t kind, n, ksteps, k_channels, cout, cin;
+    const void* src;
+    const void* src2;
+    void* dst;
+} cvae_pack_job;
+int64_t cvae_pack_elems(const cvae_pack_job* job);
+int cvae_pack_weights(const cvae_pack_job* jobs, int count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm2d + MaxPool2d(2) + ReLU/Tanh (vae_nets.py:70-72,75-77,80-82,85-87).
+ * scale_shift is fp32 [4][C] = scale | shift | mean | invstd, written by cvae_bn_finalize.
+ * `stats` ([2][C] double: sum, sum of squares of the bias-free conv output) come from
+ * CVAE_EPI_STATS.  Training mode also updates running_mean / running_var / num_batches_tracked
+ * with nn.BatchNorm2d's defaults (momentum 0.1, unbiased running variance).  act: 0 ReLU, 1 Tanh.
+ * ---------------------------------------------------------------------------------------------- */
+int cvae_bn_finalize(int channels, int64_t count, int training, const double* stats, const float* gamma,
+                     const float* beta, const float* conv_bias, float* running_mean, float* running_var,
+                     int64_t* num_batches_tracked, float momentum, float eps, float* scale_shift, void* stream);
+int cvae_bn_pool_act_fwd(int batch, int height, int width, int channels, int act, const void* conv_out,
+                         const float* scale_shift, void* out, void* stream);
+/* conv_out bf16 [B][H][W][C]; act_out, d_act bf16 [B][H/2][W/2][C]; sums: [2][C] double scratch;
+ * d_conv bf16 [B][H][W][C]; dgamma, dbeta fp32 [C] (overwritten). */
+int cvae_bn_pool_act_bwd(int batch, int height, int width, int channels, int act, const void* conv_out,
+                         const void* act_out, const void* d_act, const float* scale_shift, const float* gamma,
+                         double* sums, void* d_conv, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear layers: fc_mu || fc_var (vae_nets.py:98-99,105-109) and decoder_input (:137,143-144).
+ * act: bf16 NHWC-flattened bottleneck [B][4096]; mu_logvar fp32 [B][64] (mu | logvar);
+ * wfc / wdec are the CVAE_PACK_FC / CVAE_PACK_DECIN outputs; gradients are written in the
+ * reference's parameter layouts.
+ * ---------------------------------------------------------------------------------------------- */
+int cvae_fc_fwd(int batch, const void* act, const float* wfc, const float* bias_mu, const float* bias_var,
+                float* mu_logvar, void* stream);
+int cvae_fc_bwd(int batch, const float* d_mu_logvar, const void* act, const float* wfc, void* d_act,
+                float* dw_mu, float* dw_var, float* db_mu, float* db_var, void* stream);
+int cvae_decin_fwd(int batch, const float* z_pred, const float* wdec, void* out, void* stream);
+int cvae_decin_bwd(int batch, const void* d_out, const float* z_pred, const float* wdec, float* d_z_pred,
+                   float* dw, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latent: z = mu + eps * exp(0.5 logvar) (vae_nets.py:48-51; eps supplied by the host for parity,
+ * sample = 0 decodes the mean as evaluate() does, :43-44) and the critic-value concat (:143):
+ * z_pred fp32 [B][33] = z | pred.  Backward adds the loss's direct gradients on mu / logvar.
+ * ---------------------------------------------------------------------------------------------- */
+int cvae_latent_fwd(int batch, int sample, const float* mu_logvar, const float* eps, const float* pred,
+                    float* z_pred, void* stream);
+int cvae_latent_bwd(int batch, const float* mu_logvar, const float* eps, const float* d_z_pred,
+                    const float* dmu_ext, const float* dlogvar_ext, float* d_mu_logvar, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * vae_loss (vae_nets.py:53-62): MS-SSIM (vae_nets.py:150-247, including the upstream window sign)
+ * + KLD * kld_weight.  recon, x: fp32 NCHW [B][3][64][64]; window11: HOST pointer to the 11
+ * normalised 1-D window weights; sums: [10] double scratch; coef: [8] float scratch carried to the
+ * backward; losses: [3] = total, recon, KLD.  grad_out: device scalar (NULL = 1).
+ * ---------------------------------------------------------------------------------------------- */
+int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar, const float* window11,
+                  float kld_weight, double* sums, float* coef, float* losses, void* stream);
+int cvae_loss_bwd(int batch, const float* recon, const float* x, const float* mu_logvar, const float* window11,
+                  float kld_weight, const float* coef, const float* grad_out, float* d_recon, float* d_mu,
+                  float* d_logvar, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Adam (torch.optim.Adam defaults, vae.py:36,58) on flat fp32 buffers; `step` is a device int64
+ * counter (incremented by the call) so the launch can be replayed from a CUDA graph.
+ * grad_scale multiplies the gradient first (1/world_size after a summing all-reduce).
+ * ---------------------------------------------------------------------------------------------- */
+int cvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                   int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Critic forward (critic_net.py:15-42,66-69).  x fp32 NCHW [N][3][64][64] in [0,1]; weights: the 14
+ * state_dict tensors concatenated in key order; pred fp32 [N].
+ * ---------------------------------------------------------------------------------------------- */
+int cvae_critic_param_count(void);
+int cvae_critic_fwd(int frames, const float* x, const float* weights, float* pred, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * -video mask pipeline.  cvae_diff_grey: vae_utility.py:270-275 (recon fp32 [N][3][64][64] ->
+ * diff fp64 [N][64][64], per-frame max).  cvae_mask_iou: vae_utility.py:279-284,153-157 and the
+ * integer counts of :57-59 for a list of thresholds at once: diff_u8 / mask (for `thr`) are
+ * optional outputs, hist512 = [gt 0|1][value] uint64 scratch/output, counts int64 [nthr][3] =
+ * tp, fn, fp.  mean_max / diff_factor are the host scalars of vae_utility.py:106-110.
+ * ---------------------------------------------------------------------------------------------- */
+int cvae_diff_grey(int frames, const float* recon_hi, const float* recon_lo, double* diff, double* max_values,
+                   void* stream);
+int cvae_mask_iou(int frames, const double* diff, const uint8_t* gt, double mean_max, double diff_factor, int thr,
+                  int nthr, const int* thr_list, uint8_t* diff_u8, uint8_t* mask, uint64_t* hist512,
+                  int64_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
