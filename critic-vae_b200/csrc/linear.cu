@@ -10,39 +10,38 @@
 namespace cvae {
 
 // ---- fc forward: ml[b][j] = sum_k a[b][k] * wfc[k][j] + bias[j];  a bf16 [B][4096] ---------------
-// grid (B/8, 8 k-slices); block 256 = 64 j x 4 k-lanes; atomics combine the k-slices.
+// grid B/4; block 256 = 64 j x 4 k-lanes; the K loop is staged through shared memory in slices of
+// 512 and reduced in a fixed order, so the result is bit-reproducible run to run (no atomics).
 __global__ void fc_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restrict__ wfc,
                               const float* __restrict__ bmu, const float* __restrict__ bvar, float* __restrict__ ml) {
-    __shared__ float sa[512][8];        // [k][row] of this slice
-    __shared__ float red[4][8][64];
-    const int b0 = blockIdx.x * 8, k0 = blockIdx.y * 512;
+    __shared__ float sa[512][4];        // [k][row] of the current slice
+    __shared__ float red[4][4][64];
+    const int b0 = blockIdx.x * 4;
     const int j = threadIdx.x & 63, kl = threadIdx.x >> 6;
-    for (int i = threadIdx.x; i < 8 * 512; i += 256) {
-        const int r = i >> 9, k = i & 511;
-        sa[k][r] = (b0 + r < B) ? __bfloat162float(a[(size_t)(b0 + r) * 4096 + k0 + k]) : 0.f;
-    }
-    __syncthreads();
-    float acc[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-    for (int k = kl; k < 512; k += 4) {
-        const float w = __ldg(wfc + (size_t)(k0 + k) * 64 + j);
-        const float4 x0 = *reinterpret_cast<const float4*>(&sa[k][0]);
-        const float4 x1 = *reinterpret_cast<const float4*>(&sa[k][4]);
-        acc[0] = fmaf(w, x0.x, acc[0]); acc[1] = fmaf(w, x0.y, acc[1]);
-        acc[2] = fmaf(w, x0.z, acc[2]); acc[3] = fmaf(w, x0.w, acc[3]);
-        acc[4] = fmaf(w, x1.x, acc[4]); acc[5] = fmaf(w, x1.y, acc[5]);
-        acc[6] = fmaf(w, x1.z, acc[6]); acc[7] = fmaf(w, x1.w, acc[7]);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < 4096; k0 += 512) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * 512; i += 256) {
+            const int r = i >> 9, k = i & 511;
+            sa[k][r] = (b0 + r < B) ? __bfloat162float(a[(size_t)(b0 + r) * 4096 + k0 + k]) : 0.f;
+        }
+        __syncthreads();
+        for (int k = kl; k < 512; k += 4) {
+            const float w = __ldg(wfc + (size_t)(k0 + k) * 64 + j);
+            const float4 x0 = *reinterpret_cast<const float4*>(&sa[k][0]);
+            acc[0] = fmaf(w, x0.x, acc[0]); acc[1] = fmaf(w, x0.y, acc[1]);
+            acc[2] = fmaf(w, x0.z, acc[2]); acc[3] = fmaf(w, x0.w, acc[3]);
+        }
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) red[kl][r][j] = acc[r];
+    for (int r = 0; r < 4; ++r) red[kl][r][j] = acc[r];
     __syncthreads();
-    for (int i = threadIdx.x; i < 8 * 64; i += 256) {
-        const int r = i >> 6, jj = i & 63;
+    {
+        const int r = threadIdx.x >> 6, jj = threadIdx.x & 63;
         if (b0 + r < B) {
-            float s = red[0][r][jj] + red[1][r][jj] + red[2][r][jj] + red[3][r][jj];
-            if (blockIdx.y == 0) s += jj < 32 ? bmu[jj] : bvar[jj - 32];
-            atomicAdd(ml + (size_t)(b0 + r) * 64 + jj, s);
+            const float s = ((red[0][r][jj] + red[1][r][jj]) + (red[2][r][jj] + red[3][r][jj])) +
+                            (jj < 32 ? bmu[jj] : bvar[jj - 32]);
+            ml[(size_t)(b0 + r) * 64 + jj] = s;
         }
     }
 }
@@ -188,8 +187,7 @@ extern "C" int cvae_fc_fwd(int batch, const void* act, const float* wfc, const f
                            const float* bias_var, float* mu_logvar, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CVAE_REQUIRE(batch > 0 && act && wfc && bias_mu && bias_var && mu_logvar, CVAE_EINVAL, "fc_fwd: bad argument");
-    CVAE_CUDA(cudaMemsetAsync(mu_logvar, 0, sizeof(float) * 64 * batch, stream));
-    fc_fwd_kernel<<<dim3((batch + 7) / 8, 8), 256, 0, stream>>>(batch, (const __nv_bfloat16*)act, wfc, bias_mu, bias_var, mu_logvar);
+    fc_fwd_kernel<<<(batch + 3) / 4, 256, 0, stream>>>(batch, (const __nv_bfloat16*)act, wfc, bias_mu, bias_var, mu_logvar);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }

@@ -1,0 +1,298 @@
+"""Host-side step driver: owns the flat parameter / gradient / optimizer buffers and the per-batch
+activation workspace, and sequences the libcvae.so kernels for encode, decode, loss, backward and
+Adam.  torch is used for device memory, streams and (optionally) CUDA-graph capture only; every
+number is produced by the sm_100a kernels behind include/cvae.h.
+
+Layer table (reference lines in vae_nets.py):
+  encoder  E0..E3  Conv2d 5x5 -> BatchNorm2d -> MaxPool2d(2) -> ReLU/Tanh            :68-88
+  heads    fc_mu, fc_var Linear(4096, 32)                                            :98-99
+  decoder  decoder_input Linear(33, 4096); D0 conv; D1..D4 conv on 2x up-sampled map :116-137
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import binding as L
+
+ENC = [(3, 32, 64), (32, 64, 32), (64, 128, 16), (128, 256, 8)]          # (cin, cout, H=W of the conv)
+DEC = [(256, 128, 4), (128, 64, 4), (64, 32, 8), (32, 32, 16), (32, 3, 32)]  # (cin, cout, H=W of the conv INPUT grid)
+ENC_CONV_IDX, ENC_BN_IDX, DEC_CONV_IDX = (0, 4, 8, 12), (1, 5, 9, 13), (0, 3, 6, 9, 12)
+KLD_WEIGHT = 0.001          # vae_parameters.py:17
+BN_MOMENTUM, BN_EPS = 0.1, 1e-5
+
+
+def param_layout():
+    """(name, shape) in the order of reference `VariationalAutoencoder.parameters()`."""
+    out = []
+    for i, (ci, co, _) in enumerate(ENC):
+        out += [(f"encoder.model.{ENC_CONV_IDX[i]}.weight", (co, ci, 5, 5)), (f"encoder.model.{ENC_CONV_IDX[i]}.bias", (co,)),
+                (f"encoder.model.{ENC_BN_IDX[i]}.weight", (co,)), (f"encoder.model.{ENC_BN_IDX[i]}.bias", (co,))]
+    out += [("encoder.fc_mu.weight", (32, 4096)), ("encoder.fc_mu.bias", (32,)),
+            ("encoder.fc_var.weight", (32, 4096)), ("encoder.fc_var.bias", (32,))]
+    for i, (ci, co, _) in enumerate(DEC):
+        out += [(f"decoder.model.{DEC_CONV_IDX[i]}.weight", (co, ci, 5, 5)), (f"decoder.model.{DEC_CONV_IDX[i]}.bias", (co,))]
+    out += [("decoder.decoder_input.weight", (4096, 33)), ("decoder.decoder_input.bias", (4096,))]
+    return out
+
+
+def msssim_window():
+    """The 11 normalised window weights exactly as the reference builds them (vae_nets.py:170-173):
+    python floats -> torch.tensor (fp32) -> divide by the fp32 sum.  Note the upstream sign."""
+    k = torch.tensor([math.exp((i - 11 // 2) ** 2 / (2 * 1.5 ** 2)) for i in range(11)])
+    k = k / k.sum()
+    return (ctypes.c_float * 11)(*[float(v) for v in k])
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Workspace:
+    """Activation / gradient buffers for one batch size."""
+
+    def __init__(self, B, dev, with_grad):
+        bf, f32, f64 = torch.bfloat16, torch.float32, torch.float64
+        e = lambda *s, dtype=bf: torch.empty(*s, dtype=dtype, device=dev)
+        self.B = B
+        self.c = [e(B, h, h, co) for (_, co, h) in ENC]                 # bias-free conv outputs
+        self.a = [e(B, h // 2, h // 2, co) for (_, co, h) in ENC]       # pooled + activated
+        self.ml = e(B, 64, dtype=f32)
+        self.zc = e(B, 33, dtype=f32)
+        self.h0 = e(B, 4, 4, 256)
+        self.d = [e(B, 4, 4, 128), e(B, 8, 8, 64), e(B, 16, 16, 32), e(B, 32, 32, 32)]
+        self.recon = e(B, 3, 64, 64, dtype=f32)
+        self.stats = torch.zeros(2 * sum(co for _, co, _ in ENC), dtype=f64, device=dev)
+        self.ss = [e(4, co, dtype=f32) for (_, co, _) in ENC]
+        self.loss_sums = torch.zeros(10, dtype=f64, device=dev)
+        self.coef = torch.zeros(8, dtype=f32, device=dev)
+        self.losses = torch.zeros(3, dtype=f32, device=dev)
+        if with_grad:
+            self.d_recon = e(B, 3, 64, 64, dtype=f32)
+            self.d_mu, self.d_lv = e(B, 32, dtype=f32), e(B, 32, dtype=f32)
+            self.g_d = [torch.empty_like(t) for t in self.d]            # grads w.r.t. pre-ReLU decoder conv outputs
+            self.g_h0 = torch.empty_like(self.h0)
+            self.dzc, self.dml = e(B, 33, dtype=f32), e(B, 64, dtype=f32)
+            self.g_a = [torch.empty_like(t) for t in self.a]
+            self.g_c = [torch.empty_like(t) for t in self.c]
+            self.bn_sums = torch.zeros(2 * 256, dtype=f64, device=dev)
+
+
+class VAEEngine:
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.CvaeError("the Critic-VAE hot path only runs on CUDA (sm_100a); there is no CPU fallback")
+        self.layout = param_layout()
+        self.offsets, off = {}, 0
+        for name, shape in self.layout:
+            n = math.prod(shape)
+            self.offsets[name] = (off, n, shape)
+            off += n
+        self.n_params = off                                             # 2,583,971
+        dev = self.device
+        self.flat = torch.zeros(off, device=dev)
+        self.gflat = torch.zeros(off, device=dev)
+        self.gflat_alt = None
+        self.exp_avg = self.exp_avg_sq = None
+        self.step = torch.zeros(1, dtype=torch.int64, device=dev)
+        # BatchNorm buffers
+        self.running_mean = [torch.zeros(co, device=dev) for _, co, _ in ENC]
+        self.running_var = [torch.ones(co, device=dev) for _, co, _ in ENC]
+        self.nbt = [torch.zeros((), dtype=torch.int64, device=dev) for _ in ENC]
+        self.window = msssim_window()
+        self._build_pack_jobs()
+        self._ws = {}
+        self._wgrad_ws = None
+        self._packed_version = None
+
+    # ---- parameters ---------------------------------------------------------------------------
+    def view(self, name, buf=None):
+        off, n, shape = self.offsets[name]
+        return (self.flat if buf is None else buf)[off:off + n].view(shape)
+
+    def _build_pack_jobs(self):
+        dev = self.device
+        jobs, self.packed = [], {}
+
+        def add(key, kind, n, ksteps, kch, cout, cin, src, src2=None, dtype=torch.bfloat16, elems=None):
+            numel = elems if elems is not None else n * ksteps * 16
+            dst = torch.zeros(numel, dtype=dtype, device=dev)
+            self.packed[key] = dst
+            jobs.append(L.PackJob(kind=kind, n=n, ksteps=ksteps, k_channels=kch, cout=cout, cin=cin,
+                                  src=_ptr(src), src2=_ptr(src2), dst=_ptr(dst)))
+
+        W = lambda n: self.view(n)
+        e, d = "encoder.model.", "decoder.model."
+        add("E0f", L.PACK_PAIR8, 32, 13, 8, 32, 3, W(e + "0.weight"))
+        for i in (1, 2, 3):
+            ci, co, _ = ENC[i]
+            w = W(f"{e}{ENC_CONV_IDX[i]}.weight")
+            add(f"E{i}f", L.PACK_FWD5, co, 25 * ci // 16, ci, co, ci, w)
+            add(f"E{i}g", L.PACK_DGRAD5, ci, 25 * co // 16, co, co, ci, w)
+        w = W(d + "0.weight")
+        add("D0f", L.PACK_FWD5, 128, 25 * 16, 256, 128, 256, w)
+        add("D0g", L.PACK_DGRAD5, 256, 25 * 8, 128, 128, 256, w)
+        for i in (1, 2, 3, 4):
+            ci, co, _ = DEC[i]
+            w = W(f"{d}{DEC_CONV_IDX[i]}.weight")
+            n4 = max(16, 4 * co)
+            add(f"D{i}f", L.PACK_PHASE_FWD, n4, 9 * ci // 16, ci, co, ci, w)
+            add(f"D{i}g", L.PACK_PHASE_DGRAD, ci, 9 * n4 // 16, n4, co, ci, w)
+        add("fc", L.PACK_FC, 0, 0, 0, 0, 0, W("encoder.fc_mu.weight"), W("encoder.fc_var.weight"), torch.float32, 4096 * 64)
+        add("decin", L.PACK_DECIN, 0, 0, 0, 0, 0, W("decoder.decoder_input.weight"), W("decoder.decoder_input.bias"),
+            torch.float32, 34 * 4096)
+        self._jobs = (L.PackJob * len(jobs))(*jobs)
+
+    def pack(self):
+        L.check(L.lib.cvae_pack_weights(self._jobs, len(self._jobs), L.stream_ptr()))
+
+    def workspace(self, B, with_grad):
+        key = (B, with_grad)
+        ws = self._ws.get(key)
+        if ws is None:
+            if with_grad and (B, False) in self._ws:
+                del self._ws[(B, False)]
+            ws = self._ws[key] = Workspace(B, self.device, with_grad)
+        return ws
+
+    # ---- forward ------------------------------------------------------------------------------
+    def _conv(self, **kw):
+        d = L.ConvDesc(**{k: (_ptr(v) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
+        L.check(L.lib.cvae_conv_gemm(ctypes.byref(d), L.stream_ptr()))
+
+    def encode(self, x, training, ws, pack=True):
+        """x fp32 NCHW [B,3,64,64] -> ws.ml = mu | logvar.  vae_nets.py:101-111."""
+        B, s = ws.B, L.stream_ptr()
+        if pack:
+            self.pack()
+        if training:
+            ws.stats.zero_()
+        so = 0
+        for i, (ci, co, h) in enumerate(ENC):
+            stats = ws.stats[so:so + 2 * co]
+            so += 2 * co
+            if i == 0:
+                self._conv(batch=B, height=h, width=h, ksize=5, src_channels=8, n_total=co, loader=L.LOAD_NCHW3,
+                           epilogue=L.EPI_STATS, ktab=L.KTAB_PAIR8, src=x, wpack=self.packed["E0f"], out=ws.c[0], stats=stats)
+            else:
+                self._conv(batch=B, height=h, width=h, ksize=5, src_channels=ci, n_total=co, loader=L.LOAD_NHWC,
+                           epilogue=L.EPI_STATS, ktab=L.KTAB_GENERIC, src=ws.a[i - 1], wpack=self.packed[f"E{i}f"],
+                           out=ws.c[i], stats=stats)
+            cname, bname = f"encoder.model.{ENC_CONV_IDX[i]}", f"encoder.model.{ENC_BN_IDX[i]}"
+            L.check(L.lib.cvae_bn_finalize(co, B * h * h, int(training), _ptr(stats), _ptr(self.view(bname + ".weight")),
+                                           _ptr(self.view(bname + ".bias")), _ptr(self.view(cname + ".bias")),
+                                           _ptr(self.running_mean[i]), _ptr(self.running_var[i]), _ptr(self.nbt[i]),
+                                           BN_MOMENTUM, BN_EPS, _ptr(ws.ss[i]), s))
+            L.check(L.lib.cvae_bn_pool_act_fwd(B, h, h, co, L.ACT_TANH if i == 3 else L.ACT_RELU, _ptr(ws.c[i]),
+                                               _ptr(ws.ss[i]), _ptr(ws.a[i]), s))
+        L.check(L.lib.cvae_fc_fwd(B, _ptr(ws.a[3]), _ptr(self.packed["fc"]), _ptr(self.view("encoder.fc_mu.bias")),
+                                  _ptr(self.view("encoder.fc_var.bias")), _ptr(ws.ml), s))
+        return ws.ml
+
+    def decode(self, pred, eps, sample, ws, pack=False):
+        """ws.ml, pred fp32 [B] (+ eps fp32 [B,32]) -> ws.recon fp32 NCHW.  vae_nets.py:48-51,139-147."""
+        B, s = ws.B, L.stream_ptr()
+        if pack:
+            self.pack()
+        L.check(L.lib.cvae_latent_fwd(B, int(sample), _ptr(ws.ml), _ptr(eps), _ptr(pred), _ptr(ws.zc), s))
+        L.check(L.lib.cvae_decin_fwd(B, _ptr(ws.zc), _ptr(self.packed["decin"]), _ptr(ws.h0), s))
+        bias = lambda i: self.view(f"decoder.model.{DEC_CONV_IDX[i]}.bias")
+        self._conv(batch=B, height=4, width=4, ksize=5, src_channels=256, n_total=128, loader=L.LOAD_NHWC,
+                   epilogue=L.EPI_BIAS_RELU, ktab=L.KTAB_GENERIC, src=ws.h0, wpack=self.packed["D0f"], out=ws.d[0], bias=bias(0))
+        for i in (1, 2, 3):
+            ci, co, h = DEC[i]
+            self._conv(batch=B, height=h, width=h, ksize=3, src_channels=ci, n_total=4 * co, loader=L.LOAD_NHWC,
+                       epilogue=L.EPI_PHASE_BIAS_RELU, ktab=L.KTAB_GENERIC, src=ws.d[i - 1], wpack=self.packed[f"D{i}f"],
+                       out=ws.d[i], bias=bias(i))
+        self._conv(batch=B, height=32, width=32, ksize=3, src_channels=32, n_total=16, loader=L.LOAD_NHWC,
+                   epilogue=L.EPI_PHASE_BIAS_TANH, ktab=L.KTAB_GENERIC, src=ws.d[3], wpack=self.packed["D4f"],
+                   out=ws.recon, bias=bias(4))
+        return ws.recon
+
+    # ---- loss ---------------------------------------------------------------------------------
+    def loss_forward(self, recon, x, ml, ws, kld_weight=KLD_WEIGHT):
+        L.check(L.lib.cvae_loss_fwd(ws.B, _ptr(recon), _ptr(x), _ptr(ml), self.window, kld_weight, _ptr(ws.loss_sums),
+                                    _ptr(ws.coef), _ptr(ws.losses), L.stream_ptr()))
+        return ws.losses
+
+    def loss_backward(self, recon, x, ml, ws, grad_out=None, kld_weight=KLD_WEIGHT):
+        L.check(L.lib.cvae_loss_bwd(ws.B, _ptr(recon), _ptr(x), _ptr(ml), self.window, kld_weight, _ptr(ws.coef),
+                                    _ptr(grad_out), _ptr(ws.d_recon), _ptr(ws.d_mu), _ptr(ws.d_lv), L.stream_ptr()))
+        return ws.d_recon, ws.d_mu, ws.d_lv
+
+    # ---- backward -----------------------------------------------------------------------------
+    def _wgrad(self, g, name, **kw):
+        d = L.WgradDesc(**{k: (_ptr(v) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
+        need = int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d)))
+        if self._wgrad_ws is None or self._wgrad_ws.numel() < need:
+            self._wgrad_ws = torch.empty(max(need, 64 << 20), dtype=torch.uint8, device=self.device)
+        # A conv bias in front of BatchNorm has an exactly-zero gradient (the batch mean removes it): leave
+        # the zero-initialised slot of the flat buffer untouched instead of writing rounding noise.
+        d.dw, d.workspace = _ptr(self.view(name + ".weight", g)), _ptr(self._wgrad_ws)
+        d.dbias = None if name.startswith("encoder.") else _ptr(self.view(name + ".bias", g))
+        L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()))
+
+    def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None):
+        """Gradients of every parameter into the flat buffer `g` (default self.gflat), given the
+        gradients of the loss w.r.t. recon / mu / logvar.  Mirrors autograd through vae_nets.py:14-19."""
+        g = self.gflat if g is None else g
+        B, s = ws.B, L.stream_ptr()
+        G = lambda n: self.view(n, g)
+        dm = "decoder.model."
+        # D4 .. D1: up-sample-folded convs
+        self._wgrad(g, dm + "12", kind=L.WGRAD_SHIFT_PHASE12, batch=B, height=32, width=32, cout=3, cin=32,
+                    x=ws.d[3], dy=d_recon, dy2=ws.recon)
+        self._conv(batch=B, height=32, width=32, ksize=3, src_channels=16, n_total=32, loader=L.LOAD_S2D_NCHW3_DTANH,
+                   epilogue=L.EPI_MASK, ktab=L.KTAB_GENERIC, src=d_recon, src2=ws.recon, wpack=self.packed["D4g"],
+                   out=ws.g_d[3], act=ws.d[3])
+        for i in (3, 2, 1):
+            ci, co, h = DEC[i]
+            self._wgrad(g, f"{dm}{DEC_CONV_IDX[i]}", kind=L.WGRAD_PHASE, batch=B, height=h, width=h, cout=co, cin=ci,
+                        x=ws.d[i - 1], dy=ws.g_d[i])
+            self._conv(batch=B, height=h, width=h, ksize=3, src_channels=4 * co, n_total=ci, loader=L.LOAD_S2D,
+                       epilogue=L.EPI_MASK, ktab=L.KTAB_GENERIC, src=ws.g_d[i], wpack=self.packed[f"D{i}g"],
+                       out=ws.g_d[i - 1], act=ws.d[i - 1])
+        self._wgrad(g, dm + "0", kind=L.WGRAD_5X5, batch=B, height=4, width=4, cout=128, cin=256, x=ws.h0, dy=ws.g_d[0])
+        self._conv(batch=B, height=4, width=4, ksize=5, src_channels=128, n_total=256, loader=L.LOAD_NHWC,
+                   epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_d[0], wpack=self.packed["D0g"], out=ws.g_h0)
+        L.check(L.lib.cvae_decin_bwd(B, _ptr(ws.g_h0), _ptr(ws.zc), _ptr(self.packed["decin"]), _ptr(ws.dzc),
+                                     _ptr(G("decoder.decoder_input.weight")), _ptr(G("decoder.decoder_input.bias")), s))
+        L.check(L.lib.cvae_latent_bwd(B, _ptr(ws.ml), _ptr(eps), _ptr(ws.dzc), _ptr(d_mu), _ptr(d_lv), _ptr(ws.dml), s))
+        L.check(L.lib.cvae_fc_bwd(B, _ptr(ws.dml), _ptr(ws.a[3]), _ptr(self.packed["fc"]), _ptr(ws.g_a[3]),
+                                  _ptr(G("encoder.fc_mu.weight")), _ptr(G("encoder.fc_var.weight")),
+                                  _ptr(G("encoder.fc_mu.bias")), _ptr(G("encoder.fc_var.bias")), s))
+        em = "encoder.model."
+        for i in (3, 2, 1, 0):
+            ci, co, h = ENC[i]
+            bname, cname = f"{em}{ENC_BN_IDX[i]}", f"{em}{ENC_CONV_IDX[i]}"
+            L.check(L.lib.cvae_bn_pool_act_bwd(B, h, h, co, L.ACT_TANH if i == 3 else L.ACT_RELU, _ptr(ws.c[i]), _ptr(ws.a[i]),
+                                               _ptr(ws.g_a[i]), _ptr(ws.ss[i]), _ptr(self.view(bname + ".weight")),
+                                               _ptr(ws.bn_sums), _ptr(ws.g_c[i]), _ptr(G(bname + ".weight")),
+                                               _ptr(G(bname + ".bias")), s))
+            if i == 0:
+                self._wgrad(g, cname, kind=L.WGRAD_SHIFT_FRAMES, batch=B, height=64, width=64, cout=32, cin=3, x=x, dy=ws.g_c[0])
+            else:
+                self._wgrad(g, cname, kind=L.WGRAD_5X5, batch=B, height=h, width=h, cout=co, cin=ci, x=ws.a[i - 1], dy=ws.g_c[i])
+                self._conv(batch=B, height=h, width=h, ksize=5, src_channels=co, n_total=ci, loader=L.LOAD_NHWC,
+                           epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
+        return g
+
+    # ---- optimizer ----------------------------------------------------------------------------
+    def adam_step(self, lr, grad_scale=1.0, betas=(0.9, 0.999), eps=1e-8, g=None):
+        if self.exp_avg is None:
+            self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        g = self.gflat if g is None else g
+        L.check(L.lib.cvae_adam_step(self.n_params, _ptr(self.flat), _ptr(g), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                                     _ptr(self.step), lr, betas[0], betas[1], eps, grad_scale, L.stream_ptr()))
+
+    def critic(self, x, weights, out=None):
+        N = x.shape[0]
+        out = torch.empty(N, 1, device=self.device) if out is None else out
+        L.check(L.lib.cvae_critic_fwd(N, _ptr(x), _ptr(weights), _ptr(out), L.stream_ptr()))
+        return out
+
+    def check_fault(self):
+        L.check(L.lib.cvae_check_device_fault(L.stream_ptr()))

@@ -273,3 +273,51 @@ def iou(G, T):
     tp, fn, fp = iou_counts(G, T)
     val = 1 if tp + fn + fp == 0 else tp / (tp + fn + fp)
     return round(val, 3)
+
+
+# ----------------------------------------------------------------------------------------------
+# Precision model of the device path (test calibration only)
+# ----------------------------------------------------------------------------------------------
+class _StoreBF16(torch.autograd.Function):
+    """Round a tensor to bf16 where the device path stores it in bf16 (activations forward,
+    activation gradients backward)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+def loss_and_grads_bf16_storage(enc, dec, x, pred, eps):
+    """Same computation as loss_and_grads (fp32 math, training-mode BN, no buffer update) but with every
+    inter-layer activation, its gradient and the conv weights rounded to bf16 -- i.e. what ANY
+    implementation with bf16 tensor-core operands computes at best.  The gap between this and the
+    fp32 result is the error budget the bf16 design choice itself costs (ReLU / max-pool gates flip
+    under 2^-9 relative perturbations); the GPU tests require the kernels to stay within a small
+    factor of it."""
+    r = _StoreBF16.apply
+    wq = lambda t: t + (t.to(torch.bfloat16).float() - t).detach()
+    enc_l = {k: (v.detach().clone().requires_grad_(True) if k in PARAM_KEYS_ENC else v.clone()) for k, v in enc.items()}
+    dec_l = {k: v.detach().clone().requires_grad_(True) for k, v in dec.items()}
+    h = r(x)
+    for i, (ci, bi) in enumerate(zip(ENC_CONV, ENC_BN)):
+        h = r(F.conv2d(h, wq(enc_l[f"model.{ci}.weight"]), enc_l[f"model.{ci}.bias"], padding=PAD))
+        h = F.batch_norm(h, None, None, enc_l[f"model.{bi}.weight"], enc_l[f"model.{bi}.bias"], training=True, eps=BN_EPS)
+        h = F.max_pool2d(h, 2)
+        h = r(torch.tanh(h) if i == 3 else torch.relu(h))
+    flat = torch.flatten(h, 1)
+    mu = F.linear(flat, enc_l["fc_mu.weight"], enc_l["fc_mu.bias"])
+    logvar = F.linear(flat, enc_l["fc_var.weight"], enc_l["fc_var.bias"])
+    z = reparametrize(mu, logvar, eps)
+    h = r(F.linear(torch.cat((z, pred), 1), dec_l["decoder_input.weight"], dec_l["decoder_input.bias"]).view(-1, 256, 4, 4))
+    for i, ci in enumerate(DEC_CONV):
+        h = F.conv2d(h, wq(dec_l[f"model.{ci}.weight"]), dec_l[f"model.{ci}.bias"], padding=PAD)
+        h = F.interpolate(r(torch.relu(h)), scale_factor=2, mode="nearest") if i < 4 else torch.tanh(h)
+    losses = vae_loss(x, mu, logvar, h)
+    losses["total_loss"].backward()
+    grads = {f"encoder.{k}": enc_l[k].grad for k in PARAM_KEYS_ENC}
+    grads.update({f"decoder.{k}": dec_l[k].grad for k in PARAM_KEYS_DEC})
+    return losses, h.detach(), mu.detach(), logvar.detach(), grads

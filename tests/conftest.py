@@ -9,7 +9,17 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), os.pa
         sys.path.insert(0, p)
 
 
+def _limit_cpu_threads():
+    # the CPU oracle must not oversubscribe a shared host (GPU boxes expose many cores to few tenants)
+    try:
+        import torch
+        torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    except Exception:
+        pass
+
+
 def pytest_configure(config):
+    _limit_cpu_threads()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 

@@ -8,7 +8,6 @@ import torch
 import critic_vae_oracle as O
 import synth
 
-torch.set_num_threads(max(1, os.cpu_count() or 1))
 
 
 def _load(golden_dir, name):
