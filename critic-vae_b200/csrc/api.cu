@@ -14,6 +14,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -44,6 +48,7 @@ int* fault_flag() {
 
 extern "C" const char* cvae_last_error(void) { return cvae::g_err; }
 extern "C" int cvae_version(void) { return 100; }
+extern "C" int64_t cvae_launch_count(void) { return (int64_t)cvae::launches(); }
 
 extern "C" int cvae_check_device_fault(void* stream) {
     int* p = cvae::fault_flag();

@@ -11,6 +11,7 @@
 namespace cvae {
 
 void set_error(const char* fmt, ...);  // defined in api.cu; thread-local message buffer
+void count_launch();                   // api.cu: one tick per kernel launched by this library
 
 #define CVAE_REQUIRE(cond, code, ...)   \
     do {                                \
@@ -32,6 +33,7 @@ void set_error(const char* fmt, ...);  // defined in api.cu; thread-local messag
 
 #define CVAE_LAUNCH_CHECK()                                                              \
     do {                                                                                 \
+        cvae::count_launch();                                                            \
         cudaError_t e__ = cudaGetLastError();                                            \
         if (e__ != cudaSuccess) {                                                        \
             cvae::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \

@@ -227,6 +227,20 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
 }
 __global__ void adam_tick_kernel(long long* step) { step[0] += 1; }
 
+// uint8 HWC frames -> fp32 NCHW in [0,1]: astype(float32) / 255 then HWC->CHW, exactly
+// vae_utility.py:324-328,337-341 (adjust_values + transpose), so the bits match the reference's input.
+__global__ void frames_u8_kernel(long long n_pix, const uint8_t* __restrict__ src, float* __restrict__ dst) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i >> 12;
+        const int p = (int)(i & 4095);
+        const uint8_t* s = src + i * 3;
+        float* d = dst + f * 3 * 4096 + p;
+        d[0] = __fdiv_rn((float)s[0], 255.f);
+        d[4096] = __fdiv_rn((float)s[1], 255.f);
+        d[8192] = __fdiv_rn((float)s[2], 255.f);
+    }
+}
+
 }  // namespace cvae
 
 using namespace cvae;
@@ -303,6 +317,15 @@ extern "C" int cvae_latent_bwd(int batch, const float* mu_logvar, const float* e
     CVAE_REQUIRE(batch > 0 && mu_logvar && eps && d_z_pred && d_mu_logvar, CVAE_EINVAL, "latent_bwd: bad argument");
     latent_bwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(batch, mu_logvar, eps, d_z_pred, dmu_ext,
                                                                                  dlogvar_ext, d_mu_logvar);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_frames_u8_to_f32(int frames, const uint8_t* hwc_u8, float* nchw_f32, void* stream) {
+    CVAE_REQUIRE(frames >= 0 && (frames == 0 || (hwc_u8 && nchw_f32)), CVAE_EINVAL, "frames_u8_to_f32: bad argument");
+    if (frames == 0) return CVAE_OK;
+    const long long n = (long long)frames * 4096;
+    frames_u8_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, hwc_u8, nchw_f32);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }

@@ -91,9 +91,42 @@ __global__ void iou_counts_kernel(const unsigned long long* __restrict__ hist, i
     counts[3 * t] = tp; counts[3 * t + 1] = fn; counts[3 * t + 2] = fp;
 }
 
+// tp / fn / fp of two boolean arrays of any length (vae_utility.py:57-59)
+__global__ void iou_pair_kernel(long long n, const uint8_t* __restrict__ g, const uint8_t* __restrict__ t,
+                                unsigned long long* __restrict__ counts) {
+    unsigned int tp = 0, fn = 0, fp = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const bool a = g[i] != 0, b = t[i] != 0;
+        tp += a && b; fn += a && !b; fp += !a && b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tp += __shfl_xor_sync(0xffffffffu, tp, o);
+        fn += __shfl_xor_sync(0xffffffffu, fn, o);
+        fp += __shfl_xor_sync(0xffffffffu, fp, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (tp) atomicAdd(counts, (unsigned long long)tp);
+        if (fn) atomicAdd(counts + 1, (unsigned long long)fn);
+        if (fp) atomicAdd(counts + 2, (unsigned long long)fp);
+    }
+}
+
 }  // namespace cvae
 
 using namespace cvae;
+
+extern "C" int cvae_iou_counts(int64_t n, const uint8_t* gt, const uint8_t* mask, int64_t* counts3, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVAE_REQUIRE(n >= 0 && counts3 && (n == 0 || (gt && mask)), CVAE_EINVAL, "iou_counts: bad argument");
+    CVAE_CUDA(cudaMemsetAsync(counts3, 0, 3 * sizeof(int64_t), stream));
+    if (n == 0) return CVAE_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    iou_pair_kernel<<<(int)blocks, 256, 0, stream>>>(n, gt, mask, (unsigned long long*)counts3);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
 
 extern "C" int cvae_diff_grey(int frames, const float* recon_hi, const float* recon_lo, double* diff,
                               double* max_values, void* stream) {

@@ -76,6 +76,9 @@ _SIGS = {
     "cvae_loss_bwd": ([c_int, P, P, P, ctypes.POINTER(c_float), c_float, P, P, P, P, P, P], c_int),
     "cvae_adam_step": ([c_i64, P, P, P, P, P, c_float, c_float, c_float, c_float, c_float, P], c_int),
     "cvae_critic_param_count": ([], c_int),
+    "cvae_launch_count": ([], c_i64),
+    "cvae_iou_counts": ([c_i64, P, P, P, P], c_int),
+    "cvae_frames_u8_to_f32": ([c_int, P, P, P], c_int),
     "cvae_critic_fwd": ([c_int, P, P, P, P], c_int),
     "cvae_diff_grey": ([c_int, P, P, P, P, P], c_int),
     "cvae_mask_iou": ([c_int, P, P, c_double, c_double, c_int, c_int, P, P, P, P, P, P], c_int),

@@ -106,7 +106,7 @@ class VAEEngine:
         self._build_pack_jobs()
         self._ws = {}
         self._wgrad_ws = None
-        self._packed_version = None
+        self.profile = None
 
     # ---- parameters ---------------------------------------------------------------------------
     def view(self, name, buf=None):
@@ -159,9 +159,19 @@ class VAEEngine:
         return ws
 
     # ---- forward ------------------------------------------------------------------------------
+    def _timed(self, family, fn):
+        """Optional per-kernel-family CUDA-event timing (bench.py's roofline pass); off by default."""
+        if self.profile is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        self.profile.append((family, a, b))
+
     def _conv(self, **kw):
         d = L.ConvDesc(**{k: (_ptr(v) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
-        L.check(L.lib.cvae_conv_gemm(ctypes.byref(d), L.stream_ptr()))
+        self._timed("conv_gemm", lambda: L.check(L.lib.cvae_conv_gemm(ctypes.byref(d), L.stream_ptr())))
 
     def encode(self, x, training, ws, pack=True):
         """x fp32 NCHW [B,3,64,64] -> ws.ml = mu | logvar.  vae_nets.py:101-111."""
@@ -233,7 +243,7 @@ class VAEEngine:
         # the zero-initialised slot of the flat buffer untouched instead of writing rounding noise.
         d.dw, d.workspace = _ptr(self.view(name + ".weight", g)), _ptr(self._wgrad_ws)
         d.dbias = None if name.startswith("encoder.") else _ptr(self.view(name + ".bias", g))
-        L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()))
+        self._timed("conv_wgrad", lambda: L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr())))
 
     def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None):
         """Gradients of every parameter into the flat buffer `g` (default self.gflat), given the

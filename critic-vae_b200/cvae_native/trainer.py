@@ -1,0 +1,123 @@
+"""Training-step driver for the hot loop of the reference's train() (vae.py:40-58):
+
+    preds = critic.evaluate(images); opt.zero_grad(); out = autoencoder(images, preds)
+    losses = autoencoder.vae_loss(*out); losses['total_loss'].backward(); opt.step()
+
+as ONE replayable CUDA graph per batch size (about 75 kernel launches, no host work in between),
+with an optional NCCL gradient all-reduce between backward and Adam for data-parallel training
+(one process per GPU, PyTorch-DDP semantics: per-rank loss/grads on the local shard, Adam on the
+mean gradient; BatchNorm statistics stay per-rank).
+
+torch supplies device memory, streams, graph capture and the process group; all arithmetic is in
+libcvae.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import binding as L
+from .engine import VAEEngine
+
+
+class TrainStep:
+    """Static-buffer training step.  Feed inputs with `load_*`, run with `run()`."""
+
+    def __init__(self, vae, critic, batch, lr=5e-5, use_graph=True, process_group=None):
+        self.vae, self.critic, self.B, self.lr = vae, critic, int(batch), float(lr)
+        self.eng: VAEEngine = vae._bind()
+        dev = self.eng.device
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.x = torch.zeros(self.B, 3, 64, 64, device=dev)
+        self.x_u8 = torch.zeros(self.B, 64, 64, 3, dtype=torch.uint8, device=dev)
+        self.eps = torch.zeros(self.B, 32, device=dev)
+        self.pred = torch.zeros(self.B, device=dev)
+        self.ws = self.eng.workspace(self.B, True)
+        self.critic_w = critic._weights() if critic is not None else None
+        self.losses = self.ws.losses
+        self._graphs = None
+        self._use_graph = use_graph
+        self.launches_per_step = None
+
+    # ---- the work ---------------------------------------------------------------------------------
+    def _front(self, from_u8):
+        eng, ws, s = self.eng, self.ws, L.stream_ptr()
+        if from_u8:
+            L.check(L.lib.cvae_frames_u8_to_f32(self.B, self.x_u8.data_ptr(), self.x.data_ptr(), s))
+        if self.critic_w is not None:
+            L.check(L.lib.cvae_critic_fwd(self.B, self.x.data_ptr(), self.critic_w.data_ptr(), self.pred.data_ptr(), s))
+        eng.encode(self.x, True, ws)
+        eng.decode(self.pred, self.eps, True, ws)
+        eng.loss_forward(ws.recon, self.x, ws.ml, ws)
+        eng.loss_backward(ws.recon, self.x, ws.ml, ws)
+        eng.backward(self.x, self.eps, ws, ws.d_recon, ws.d_mu, ws.d_lv)
+
+    def _back(self):
+        self.eng.adam_step(self.lr, grad_scale=1.0 / self.world)
+
+    def _eager(self, from_u8):
+        self._front(from_u8)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
+        self._back()
+
+    def _capture(self, from_u8):
+        # warm-up on a side stream (allocations, cudaFuncSetAttribute, Adam state) -- results are
+        # discarded by restoring parameters, optimizer state and BN buffers afterwards
+        eng = self.eng
+        keep = [eng.flat.clone(), eng.step.clone()] + [t.clone() for t in eng.running_mean + eng.running_var] + \
+               [t.clone() for t in eng.nbt]
+        had_state = eng.exp_avg is not None
+        if had_state:
+            keep_m, keep_v = eng.exp_avg.clone(), eng.exp_avg_sq.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            n0 = L.lib.cvae_launch_count()
+            self._eager(from_u8)
+            self.launches_per_step = int(L.lib.cvae_launch_count() - n0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        eng.check_fault()
+        g_front, g_back = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_front):
+            self._front(from_u8)
+        with torch.cuda.graph(g_back):
+            self._back()
+        # undo the warm-up step
+        eng.flat.copy_(keep[0]); eng.step.copy_(keep[1])
+        n = len(eng.running_mean)
+        for i in range(n):
+            eng.running_mean[i].copy_(keep[2 + i]); eng.running_var[i].copy_(keep[2 + n + i]); eng.nbt[i].copy_(keep[2 + 2 * n + i])
+        if had_state:
+            eng.exp_avg.copy_(keep_m); eng.exp_avg_sq.copy_(keep_v)
+        else:
+            eng.exp_avg.zero_(); eng.exp_avg_sq.zero_()
+        return g_front, g_back
+
+    # ---- public -----------------------------------------------------------------------------------
+    def load(self, frames=None, eps=None, frames_u8=None, non_blocking=True):
+        """Copy one batch into the static buffers.  `frames`: fp32 (B,3,64,64) in [0,1] (host or device);
+        `frames_u8`: uint8 (B,64,64,3) as MineRL delivers them, converted on the device."""
+        if frames is not None:
+            self.x.copy_(frames, non_blocking=non_blocking)
+        if frames_u8 is not None:
+            self.x_u8.copy_(frames_u8, non_blocking=non_blocking)
+        if eps is not None:
+            self.eps.copy_(eps, non_blocking=non_blocking)
+
+    def run(self, from_u8=False):
+        """One optimizer step on the loaded batch.  Returns the device tensor [total, recon, KLD]."""
+        if not self._use_graph:
+            self._eager(from_u8)
+            return self.losses
+        if self._graphs is None:
+            self._graphs = {}
+        gs = self._graphs.get(from_u8)
+        if gs is None:
+            gs = self._graphs[from_u8] = self._capture(from_u8)
+        gs[0].replay()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
+        gs[1].replay()
+        return self.losses

@@ -29,6 +29,8 @@ extern "C" {
 
 const char* cvae_last_error(void);
 int cvae_version(void);
+/* Kernels launched by this library in this process so far (bench.py reports the per-step count). */
+int64_t cvae_launch_count(void);
 /* Reads and clears the device-side fault flag raised by bounded waits.  Synchronises `stream`. */
 int cvae_check_device_fault(void* stream);
 
@@ -185,6 +187,10 @@ int cvae_loss_bwd(int batch, const float* recon, const float* x, const float* mu
 int cvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                    int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* uint8 HWC frames [N][64][64][3] -> fp32 NCHW [N][3][64][64] = astype(float32) / 255, the
+ * preprocessing of vae_utility.py:324-343 (adjust_values + HWC->CHW) done on the device. */
+int cvae_frames_u8_to_f32(int frames, const uint8_t* hwc_u8, float* nchw_f32, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Critic forward (critic_net.py:15-42,66-69).  x fp32 NCHW [N][3][64][64] in [0,1]; weights: the 14
  * state_dict tensors concatenated in key order; pred fp32 [N].
@@ -204,6 +210,9 @@ int cvae_diff_grey(int frames, const float* recon_hi, const float* recon_lo, dou
 int cvae_mask_iou(int frames, const double* diff, const uint8_t* gt, double mean_max, double diff_factor, int thr,
                   int nthr, const int* thr_list, uint8_t* diff_u8, uint8_t* mask, uint64_t* hist512,
                   int64_t* counts, void* stream);
+/* get_iou's integer part (vae_utility.py:57-59) for two boolean (uint8 0/1) arrays of n elements:
+ * counts3 = tp, fn, fp.  The division and round(.,3) stay in Python. */
+int cvae_iou_counts(int64_t n, const uint8_t* gt, const uint8_t* mask, int64_t* counts3, void* stream);
 
 #ifdef __cplusplus
 }
