@@ -1,0 +1,177 @@
+"""CPU-only checks: the C ABI loads and exports every symbol include/cvae.h declares (no compute calls
+without a GPU), argument validation, host-side logic of the drop-in, and the data-parallel plumbing on
+a world_size-2 gloo group."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import cvae_native.binding as L
+    header = open(os.path.join(ROOT, "include", "cvae.h")).read()
+    declared = set(re.findall(r"\b(cvae_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(L.lib, name), f"{name} declared in include/cvae.h but not exported by libcvae.so"
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    assert L.lib.cvae_version() >= 100
+    assert L.lib.cvae_critic_param_count() == 11873
+
+
+def test_argument_validation_without_gpu():
+    import cvae_native.binding as L
+    assert L.lib.cvae_conv_gemm(None, None) == -1 and b"null descriptor" in L.lib.cvae_last_error()
+    d = L.ConvDesc(batch=1, height=8, width=8, ksize=4, src_channels=16, n_total=16)
+    assert L.lib.cvae_conv_gemm(ctypes.byref(d), None) == -1 and b"ksize" in L.lib.cvae_last_error()
+    d = L.ConvDesc(batch=1, height=8, width=8, ksize=5, src_channels=16, n_total=24, src=1, wpack=1, out=1)
+    assert L.lib.cvae_conv_gemm(ctypes.byref(d), None) == -1
+    assert L.lib.cvae_adam_step(0, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1.0, None) == -1
+    assert L.lib.cvae_mask_iou(-1, None, None, 1.0, 1.0, 50, 0, None, None, None, None, None, None) == -1
+    assert L.lib.cvae_conv_ksteps(5, 64, L.KTAB_GENERIC) == 100 and L.lib.cvae_conv_ksteps(5, 8, L.KTAB_PAIR8) == 13
+    with pytest.raises(L.CvaeError):
+        L.check(-1)
+
+
+def test_no_cpu_fallback():
+    import cvae_native.binding as L
+    import vae_nets
+    from cvae_native.engine import VAEEngine
+    with pytest.raises(L.CvaeError):
+        VAEEngine("cpu")
+    vae = vae_nets.VariationalAutoencoder()
+    with pytest.raises(L.CvaeError):
+        vae(torch.zeros(1, 3, 64, 64), torch.zeros(1, 1))
+
+
+def test_parameter_layout_matches_reference_module_order():
+    import vae_nets
+    from cvae_native.engine import param_layout
+    vae = vae_nets.VariationalAutoencoder()
+    names = [(n, tuple(p.shape)) for n, p in vae.named_parameters()]
+    assert names == [(n, tuple(s)) for n, s in param_layout()]
+    assert sum(p.numel() for p in vae.parameters()) == 2583971
+    enc_keys = set(vae.encoder.state_dict())
+    assert {"model.0.weight", "model.1.running_mean", "model.13.num_batches_tracked", "fc_mu.weight", "fc_var.bias"} <= enc_keys
+    assert set(vae.decoder.state_dict()) == {f"model.{i}.{p}" for i in (0, 3, 6, 9, 12) for p in ("weight", "bias")} | \
+        {"decoder_input.weight", "decoder_input.bias"}
+
+
+def test_phase_decomposition_equals_conv_on_upsampled_input():
+    """conv5x5(nearest_up2(x)) == depth_to_space(conv3x3 with the folded weights): the identity the
+    decoder kernels rely on (vae_nets.py:119-133), checked in fp64 on the CPU."""
+    import packref
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 6, 5, 7, generator=g, dtype=torch.float64)
+    W = torch.randn(4, 6, 5, 5, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), W, padding=2)
+    Weff = packref.phase_weights(W).reshape(2, 2, 4, 3, 3, 6)
+    out = torch.zeros_like(ref)
+    for a in (0, 1):
+        for b in (0, 1):
+            out[:, :, a::2, b::2] = F.conv2d(x, Weff[a, b].permute(0, 3, 1, 2), padding=1)
+    assert torch.allclose(out, ref, atol=1e-12)
+
+
+def test_select_balanced_matches_reference_loop():
+    """vae_utility.py:431-457 restated directly vs the drop-in helper."""
+    import vae_utility as U
+    rng = np.random.default_rng(0)
+    preds = rng.uniform(0, 1, 2000).tolist()
+    for collect in (3, 150):
+        c_high = c_mid = c_low = 0
+        want = []
+        for i, pred in enumerate(preds):
+            if c_high >= collect and c_low >= collect and c_mid >= collect:
+                break
+            elif 0.4 <= pred <= 0.6 and c_mid < collect:
+                want.append((i, "mid")); c_mid += 1
+            elif pred >= 0.7 and c_high < collect:
+                want.append((i, "high")); c_high += 1
+            elif pred <= 0.25 and c_low < collect:
+                want.append((i, "low")); c_low += 1
+        assert U.select_balanced(preds, collect) == want
+
+
+def test_host_side_mask_helpers():
+    import vae_utility as U
+    import critic_vae_oracle as O
+    mx = [np.float64(v) for v in (0.25, 0.5, 0.125)]
+    assert U.get_diff_factor(mx) == O.diff_factor(mx)
+    assert U.get_diff_factor([np.float64(0.0)]) == (0, 0.0)
+    d = np.array([[0.1, 0.9], [0.4, 0.2]])
+    assert np.array_equal(U.prepare_diff(d.copy(), 2.0, 0.5), np.array([[0.2, 1.0], [0.8, 0.4]]))
+    assert U._iou_from_counts(0, 0, 0) == 1 and U._iou_from_counts(1, 1, 1) == 0.333
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import critic_vae_oracle as O
+    torch.manual_seed(0)
+    torch.set_num_threads(2)
+    # identical weights and permutation on every rank, contiguous 1/world slice of each global batch
+    w = torch.linspace(-1, 1, 64)
+    data = torch.arange(40 * 64, dtype=torch.float32).reshape(40, 64) / 1000.0
+    order = torch.as_tensor(np.random.default_rng(0).permutation(40))
+    seen, m, v = [], torch.zeros(64), torch.zeros(64)
+    for step, b0 in enumerate(range(0, 40, 16)):           # global batch 16, last one short (8)
+        idx = order[b0:b0 + 16]
+        per = (idx.numel() + world - 1) // world
+        mine = idx[rank * per:(rank + 1) * per]
+        seen += mine.tolist()
+        g_local = (data[mine] * (data[mine] @ w)[:, None]).mean(0) if mine.numel() else torch.zeros(64)
+        flat = g_local.clone()
+        dist.all_reduce(flat)                                # what TrainStep does with eng.gflat
+        O.adam_step(w, flat / world, m, v, step + 1)         # grad_scale = 1 / world inside cvae_adam_step
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (seen, w.clone()))
+    if rank == 0:
+        out.put(gathered)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_plumbing_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (seen0, w0), (seen1, w1) = res
+    assert sorted(seen0 + seen1) == list(range(40))          # every sample exactly once per epoch
+    assert torch.equal(w0, w1)                               # replicas stay bit-identical
+    # equals Adam on the mean of the per-rank gradients computed in one process
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import critic_vae_oracle as O
+    w = torch.linspace(-1, 1, 64)
+    data = torch.arange(40 * 64, dtype=torch.float32).reshape(40, 64) / 1000.0
+    order = torch.as_tensor(np.random.default_rng(0).permutation(40))
+    m, v = torch.zeros(64), torch.zeros(64)
+    for step, b0 in enumerate(range(0, 40, 16)):
+        idx = order[b0:b0 + 16]
+        per = (idx.numel() + 1) // 2
+        gs = [(data[s] * (data[s] @ w)[:, None]).mean(0) for s in (idx[:per], idx[per:2 * per])]
+        O.adam_step(w, (gs[0] + gs[1]) / 2, m, v, step + 1)
+    assert torch.allclose(w, w0, atol=1e-7)
