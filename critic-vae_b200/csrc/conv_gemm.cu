@@ -142,13 +142,21 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
                     alive = mbar_wait(&bar_full[ring_stage], ring_phase, a.fault);
                     tc_fence_after();
                     const uint32_t wb = wring_addr + ring_stage * stage_bytes;
-                    for (int t = 0; t < a.tm; ++t) {
-                        for (int ks = 0; ks < a.ksps; ++ks) {
-                            const int kidx = st * a.ksps + ks;
-                            const uint2 e = ktab[kidx];
-                            const uint64_t da = smem_desc(planes_addr + (uint32_t)t * 2048u + e.x, e.y, 128u);
-                            const uint64_t db = smem_desc(wb + (uint32_t)ks * N * 32u, 128u, 256u);
-                            umma_bf16(tmem_base + (uint32_t)t * N, da, db, idesc, kidx > 0);
+                    // One elected thread feeds the tensor pipe, so the issue loop must stay at a handful
+                    // of instructions per MMA: descriptors are built once per K step and the tile index
+                    // only bumps the 16-byte-granular start-address field (2048 B per 128-pixel tile).
+                    for (int ks = 0; ks < a.ksps; ++ks) {
+                        const int kidx = st * a.ksps + ks;
+                        const uint2 e = ktab[kidx];
+                        uint64_t da = smem_desc(planes_addr + e.x, e.y, 128u);
+                        const uint64_t db = smem_desc(wb + (uint32_t)ks * N * 32u, 128u, 256u);
+                        const uint32_t accumulate = kidx > 0 ? 1u : 0u;
+                        uint32_t tcol = tmem_base;
+#pragma unroll 4
+                        for (int t = 0; t < a.tm; ++t) {
+                            umma_bf16(tcol, da, db, idesc, accumulate);
+                            da += 128;   // (2048 >> 4)
+                            tcol += N;
                         }
                     }
                     umma_commit(&bar_empty[ring_stage]);
@@ -295,11 +303,21 @@ static int launch(const ConvArgs& a, size_t smem, cudaStream_t stream) {
         CVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    int per_sm = (smem > 100 * 1024 || a.tm * N > 256) ? 1 : 2;
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)(a.tm * N)) ncols <<= 1;
+    int per_sm = (int)((228 * 1024) / (smem + 2048));          // shared-memory limit (1 KB static + 1 KB reserved per CTA)
+    if (per_sm > (int)(512 / ncols)) per_sm = (int)(512 / ncols);  // TMEM limit
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
     int gx = sm_count() * per_sm / a.n_blocks;
     if (gx < 1) gx = 1;
     if (gx > a.num_chunks) gx = a.num_chunks;
     dim3 grid(gx, a.n_blocks);
+    static const bool debug = getenv("CVAE_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "conv_gemm<L%d,E%d,N%d> B=%d %dx%d planes=%d ksteps=%d ksps=%d stages=%d tm=%d chunks=%d smem=%zu "
+                        "cols=%u per_sm=%d grid=(%d,%d)\n", LOADER, EPI, N, a.B, a.H, a.W, a.planes, a.ksteps, a.ksps,
+                a.nstages, a.tm, a.num_chunks, smem, ncols, per_sm, gx, a.n_blocks);
     kern<<<grid, kThreads, smem, stream>>>(a);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
@@ -344,33 +362,39 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     a.ps = PlaneSrc{a.B, a.H, a.W, a.pad, a.PW, a.IH, a.planes,
                     (d->loader == CVAE_LOAD_S2D) ? d->src_channels / 4 : d->src_channels, 0, d->src, d->src2};
 
-    // K steps per weight stage: a whole tap when it fits in <= 16 KB, else 64 channels' worth
+    // Tiling policy.  Phases inside a CTA are sequential (load planes -> MMA -> epilogue), so overlap
+    // comes from co-resident CTAs: aim for >= 2 CTAs per SM (<= 112 KB of shared memory and <= 256
+    // TMEM columns each), with as many 128-pixel tiles per pass as fit -- every tile of a pass reuses
+    // the same weight stage, so `tm` divides the L2 -> SM weight traffic.
     if (d->ktab == CVAE_KTAB_PAIR8) a.ksps = 13;
     else {
-        int per_tap = d->src_channels / 16;
-        a.ksps = per_tap;
-        while (a.ksps * N * 32 > 16 * 1024 && a.ksps % 2 == 0) a.ksps /= 2;
+        a.ksps = d->src_channels / 16;                       // one tap
+        while (a.ksps * N * 32 > 8 * 1024 && a.ksps % 2 == 0) a.ksps /= 2;
     }
     CVAE_REQUIRE(a.ksteps % a.ksps == 0, CVAE_EINVAL, "conv_gemm: internal stage split");
-    a.nstages = 4;
     const size_t stage_bytes = (size_t)a.ksps * N * 32;
 
     const long total_v = (long)a.B * a.IH * a.PW - (long)a.pad * a.PW;  // pixels from first to last valid row
     const int total_tiles = (int)((total_v + 127) / 128);
-    const size_t smem_cap = 200 * 1024;
+    auto smem_for = [&](int tm, int nstages) {
+        const size_t L = (size_t)tm * 128 + 2 * a.halo + 8;
+        return (((size_t)a.planes * L * 16 + 1023) & ~(size_t)1023) + nstages * stage_bytes + (size_t)a.ksteps * 8 + 64;
+    };
     int tm = d->tm > 0 ? d->tm : (256 / N > 0 ? 256 / N : 1);
     if (tm > 8) tm = 8;
     if (tm > total_tiles) tm = total_tiles;
-    size_t smem = 0;
-    for (;; --tm) {
-        CVAE_REQUIRE(tm >= 1, CVAE_EINVAL, "conv_gemm: shape does not fit shared memory");
-        a.tm = tm;
-        a.L = tm * 128 + 2 * a.halo + 8;
-        a.plane_stride = a.L * 16;
-        smem = (((size_t)a.planes * a.plane_stride + 1023) & ~(size_t)1023) + a.nstages * stage_bytes +
-               (size_t)a.ksteps * 8 + 64;
-        if (smem <= smem_cap && tm * N <= 512) break;
+    a.nstages = 3;
+    const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024;
+    if (d->tm <= 0) {
+        while (tm > 1 && smem_for(tm, 3) > two_per_sm) --tm;
+        if (smem_for(tm, 3) > two_per_sm && smem_for(tm, 2) <= two_per_sm) a.nstages = 2;
     }
+    while (tm > 1 && (smem_for(tm, a.nstages) > one_per_sm || tm * N > 512)) --tm;
+    CVAE_REQUIRE(smem_for(tm, a.nstages) <= one_per_sm && tm * N <= 512, CVAE_EINVAL, "conv_gemm: shape does not fit shared memory");
+    a.tm = tm;
+    a.L = tm * 128 + 2 * a.halo + 8;
+    a.plane_stride = a.L * 16;
+    const size_t smem = smem_for(tm, a.nstages);
     a.num_chunks = (total_tiles + a.tm - 1) / a.tm;
     CVAE_REQUIRE((size_t)a.planes * a.plane_stride < (1u << 18), CVAE_EINVAL, "conv_gemm: planes exceed descriptor range");
 

@@ -236,6 +236,50 @@ __global__ void wgrad_fold_kernel(const FoldArgs f) {
     }
 }
 
+// Bandwidth-shaped fold for the 5X5 / PHASE kinds: one thread per (tap, co, ci) with ci fastest, so the
+// reads of every split are coalesced row segments and the split loop carries four independent loads;
+// the OIHW write is a 100-byte-strided scatter of 4-byte values (10 MB per step in total).
+__global__ void __launch_bounds__(256) wgrad_fold_rows_kernel(const FoldArgs f) {
+    const int total = 25 * f.cout * f.cin;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < total) {
+        const int ci = idx % f.cin, co = (idx / f.cin) % f.cout, tap = idx / (f.cin * f.cout);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const size_t ss = (size_t)f.split_floats;
+        auto accumulate = [&](size_t off) {
+            const float* p = f.partial + off;
+            int s = 0;
+            for (; s + 4 <= f.splits; s += 4) {
+                a0 += __ldg(p + (size_t)s * ss);
+                a1 += __ldg(p + (size_t)(s + 1) * ss);
+                a2 += __ldg(p + (size_t)(s + 2) * ss);
+                a3 += __ldg(p + (size_t)(s + 3) * ss);
+            }
+            for (; s < f.splits; ++s) a0 += __ldg(p + (size_t)s * ss);
+        };
+        if (f.kind == CVAE_WGRAD_5X5) {
+            accumulate(((size_t)tap * f.m_total + co) * f.n + ci);
+        } else {
+            const int ky = tap / 5, kx = tap - ky * 5;
+#pragma unroll
+            for (int ab = 0; ab < 4; ++ab) {
+                const int t = phase_tap(ab >> 1, ky) * 3 + phase_tap(ab & 1, kx);
+                accumulate(((size_t)t * f.m_total + ab * f.cout + co) * f.n + ci);
+            }
+        }
+        f.dw[((size_t)co * f.cin + ci) * 25 + tap] = (a0 + a1) + (a2 + a3);
+    } else if (idx < total + f.cout && f.dbias != nullptr) {
+        const int co = idx - total;
+        float acc = 0.f;
+        for (int s = 0; s < f.splits; ++s) {
+            const float* p = f.partial + (size_t)s * f.split_floats + f.bias_off;
+            if (f.kind == CVAE_WGRAD_5X5) acc += p[(size_t)co * 16];
+            else for (int ab = 0; ab < 4; ++ab) acc += p[(size_t)(ab * f.cout + co) * 16];
+        }
+        f.dbias[co] = acc;
+    }
+}
+
 template <int LA, int LB>
 static int launch_wgrad(const WgradArgs& a, size_t smem, dim3 grid, cudaStream_t stream) {
     auto kern = conv_wgrad_kernel<LA, LB>;
@@ -418,8 +462,13 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
 
     f.kind = d->kind; f.cout = d->cout; f.cin = d->cin; f.splits = splits; f.split_floats = a.split_floats;
     f.m_total = a.m_total; f.n = n; f.partial = a.partial; f.dw = (float*)d->dw; f.dbias = (float*)d->dbias;
-    const int total = d->cout * d->cin * 25 + d->cout;
-    wgrad_fold_kernel<<<(total + 255) / 256, 256, 0, stream>>>(f);
+    if (d->kind == CVAE_WGRAD_5X5 || d->kind == CVAE_WGRAD_PHASE) {
+        const int total = d->cout * d->cin * 25 + d->cout;
+        wgrad_fold_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(f);
+    } else {
+        const int total = d->cout * d->cin * 25 + d->cout;
+        wgrad_fold_kernel<<<(total + 255) / 256, 256, 0, stream>>>(f);
+    }
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
