@@ -1,13 +1,26 @@
 // Implicit-GEMM 5x5 / 3x3 convolution on tcgen05 for 64x64-and-smaller feature maps.
 //
-// Layout idea ("halo planes"): the CTA's slice of the input is staged ONCE in shared memory as
-// planes [channel/8][virtual pixel][8 channels], i.e. in the no-swizzle UMMA core-matrix layout
-// with pixels as rows.  Images are laid out in a linear "virtual pixel" space with `pad` shared
-// zero columns per row and `pad` shared zero rows per image, so the A operand of every filter tap
-// is the SAME shared-memory tile read through a descriptor whose start address is shifted by
+// Layout idea ("halo planes"): the CTA's slice of the input is staged in shared memory as planes
+// [channel/8][virtual pixel][8 channels], i.e. in the no-swizzle UMMA core-matrix layout with
+// pixels as rows.  Images are laid out in a linear "virtual pixel" space with `pad` shared zero
+// columns per row and `pad` shared zero rows per image, so the A operand of every filter tap is the
+// SAME shared-memory tile read through a descriptor whose start address is shifted by
 // (dy*PW + dx) pixels.  No im2col, no re-fetch per tap: 25x (9x) reuse out of shared memory.
-// Weights stream through a small mbarrier ring filled by cp.async.bulk and are reused by all
-// `tm` 128-pixel tiles of the pass, whose accumulators sit side by side in TMEM.
+//
+// Pipeline (conv_pipe_kernel, one persistent CTA per SM, 10 warps):
+//   warps 4-7  plane producers: cp.async 16-byte copies global -> plane buffer (zero-fill for the
+//              padding), two buffers, one (pixel chunk, channel group) each
+//   warp  8    weight producer: cp.async.bulk of packed K-step blocks into a deep mbarrier ring
+//              (the ring has to cover L2 latency x 64/tm bytes per clock)
+//   warp  9    one elected thread issues tcgen05.mma: `tm` 128-pixel tiles share every weight stage,
+//              their accumulators sit side by side in TMEM; two accumulator sets alternate
+//   warps 0-3  epilogue: tcgen05.ld -> bias / activation / BatchNorm statistics / ReLU mask ->
+//              global, overlapped with the MMAs of the next work item
+// Work item = (pixel chunk of tm*128 virtual pixels, N block); channel groups of <= 128 channels
+// are accumulated into the same TMEM tile so the plane buffers stay <= ~80 KB each.
+//
+// conv_gemm_kernel (the first, phase-sequential version) remains for the two loaders that convert
+// fp32 NCHW tensors on the fly (frames, d_recon) and therefore cannot use cp.async.
 //
 // Reference ops replaced: nn.Conv2d(5,1,2) at vae_nets.py:69,74,79,84,117,121,125,129,133, the
 // nn.Upsample(2) at :119,123,127,131 (folded: conv5x5(up2(x)) == depth_to_space(conv3x3_4C(x)))
@@ -21,17 +34,26 @@ namespace cvae {
 struct ConvArgs {
     int B, H, W, pad, KW;
     int PW, IH;          // W + pad, H + pad
-    int planes;          // 8-channel planes of the A operand
-    int n_blocks;        // N split (blockIdx.y)
+    int planes;          // 8-channel planes of one channel group (= all planes in the sequential kernel)
+    int ncg;             // channel groups
+    int n_blocks;        // N blocks of the kernel (work items per chunk)
     int c_total;         // n_total
-    int ksteps, ksps;    // K=16 steps in total / per weight stage
+    int nb_pack;         // N block of the packed weights (min(n_total, 128))
+    int ksteps;          // K=16 steps over all channel groups
+    int kpg;             // K steps per channel group
+    int ksps;            // K steps per weight stage
     int tm;              // tiles per pass
     int num_chunks;
     int halo;            // pad*PW + pad
     int L;               // pixels per plane (tm*128 + 2*halo + 8)
     int plane_stride;    // bytes
+    int buf_bytes;       // bytes of one plane buffer (pipelined kernel)
     int ktab_mode;
     int nstages;
+    int resident;        // whole weight matrix lives in the ring (loaded once)
+    int kgroup;          // K steps issued per unrolled group (divides planes/2 and ksps)
+    int rotate;          // CTAs start the K loop at different weight stages (spreads the L2 reads of the shared weights)
+    FastDiv dPW, dIH;
     PlaneSrc ps;         // where the A-operand planes come from
     const __nv_bfloat16* wpack;
     void* out;
@@ -39,18 +61,439 @@ struct ConvArgs {
     const __nv_bfloat16* act;
     double* stats;
     int* fault;
+    int dbg_flags;            // experiments: 1 = skip epilogue work, 2 = fill planes only once per buffer
+    unsigned long long* dbg;  // optional per-CTA cycle counters [grid][8] (cvae_conv_debug_counters)
 };
 
-static constexpr int kThreads = 192;  // warps 0-3: loader + epilogue, 4: weight producer, 5: MMA
+// K-step table entry: x = byte offset of the A tile inside the plane buffer, y = LBO (bytes)
+__device__ __forceinline__ uint2 ktab_entry(const ConvArgs& a, int i) {
+    uint2 e;
+    if (a.ktab_mode == CVAE_KTAB_GENERIC) {
+        const int cpairs = a.planes >> 1;
+        const int tap = i / cpairs, cp = i - tap * cpairs;
+        const int dy = tap / a.KW - a.pad, dx = tap % a.KW - a.pad;
+        e.x = (uint32_t)(a.halo + dy * a.PW + dx) * 16u + (uint32_t)cp * 2u * a.plane_stride;
+        e.y = (uint32_t)a.plane_stride;
+    } else {  // PAIR8: 5x5 taps of an 8-channel source, two taps per K step
+        if (i < 10) {
+            const int ky = i >> 1, kx = (i & 1) * 2;
+            e.x = (uint32_t)(a.halo + (ky - 2) * a.PW + (kx - 2)) * 16u;
+            e.y = 16u;
+        } else if (i < 12) {
+            const int ky = (i - 10) * 2;
+            e.x = (uint32_t)(a.halo + (ky - 2) * a.PW + 2) * 16u;
+            e.y = (uint32_t)a.PW * 16u;
+        } else {
+            e.x = (uint32_t)(a.halo + 2 * a.PW + 2) * 16u;
+            e.y = 16u;
+        }
+    }
+    return e;
+}
 
 // --------------------------------------------------------------------------------------------
-// kernel
+// epilogue of one 128-pixel tile: warp w owns TMEM lanes [32w, 32w+32) = rows of the tile
 // --------------------------------------------------------------------------------------------
+template <int EPI, int N>
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t tmem_tile, int v_tile, int nb, int warp, int lane,
+                                              float* s1, float* s2, float* stat_scratch) {
+    const int v = v_tile + warp * 32 + lane;
+    int vrow = v / a.PW;
+    int vcol = v - vrow * a.PW;
+    int n = vrow / a.IH;
+    int r = vrow - n * a.IH;
+    const bool valid = (vcol < a.W) && (r >= a.pad) && (n < a.B);
+    const int h = r - a.pad, w = vcol;
+    const size_t pix = ((size_t)n * a.H + h) * a.W + w;
+#pragma unroll
+    for (int g = 0; g < N / 16; ++g) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_tile + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 16), raw);
+        tmem_wait_ld();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(raw[i]);
+        const int c0 = nb * N + g * 16;  // first global output column of this group
+
+        if constexpr (EPI == CVAE_EPI_STATS) {
+            uint32_t p[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+            float* sc = stat_scratch + warp * 32 * 17;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sc[lane * 17 + 2 * i] = valid ? bf16_lo(p[i]) : 0.f;
+                sc[lane * 17 + 2 * i + 1] = valid ? bf16_hi(p[i]) : 0.f;
+            }
+            __syncwarp();
+            const int col = lane & 15, half = lane >> 4;
+            float sa = 0.f, sb = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+                const float x = sc[(half * 16 + rr) * 17 + col];
+                sa += x;
+                sb += x * x;
+            }
+            sa += __shfl_xor_sync(0xffffffffu, sa, 16);
+            sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+            s1[g] += sa;
+            s2[g] += sb;
+            __syncwarp();
+            if (valid) {
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.c_total + c0);
+                o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+            }
+        } else if constexpr (EPI == CVAE_EPI_BIAS_RELU || EPI == CVAE_EPI_PLAIN || EPI == CVAE_EPI_MASK) {
+            if (valid) {
+                if constexpr (EPI == CVAE_EPI_BIAS_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i] + __ldg(a.bias + c0 + i), 0.f);
+                }
+                if constexpr (EPI == CVAE_EPI_MASK) {
+                    const uint4* m = reinterpret_cast<const uint4*>(a.act + pix * a.c_total + c0);
+                    const uint4 m0 = __ldg(m), m1 = __ldg(m + 1);
+                    const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (!(bf16_lo(mm[i]) > 0.f)) f[2 * i] = 0.f;
+                        if (!(bf16_hi(mm[i]) > 0.f)) f[2 * i + 1] = 0.f;
+                    }
+                }
+                uint32_t p[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.c_total + c0);
+                o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+            }
+        } else if constexpr (EPI == CVAE_EPI_PHASE_BIAS_RELU) {
+            if (valid) {
+                const int cout = a.c_total >> 2;
+                const int ab = c0 / cout, co = c0 - ab * cout;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i] + __ldg(a.bias + co + i), 0.f);
+                uint32_t p[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+                const size_t opix = ((size_t)n * 2 * a.H + 2 * h + (ab >> 1)) * (2 * a.W) + 2 * w + (ab & 1);
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + opix * cout + co);
+                o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+            }
+        } else {  // CVAE_EPI_PHASE_BIAS_TANH: 12 of the 16 columns are (a,b,c)
+            if (valid) {
+                float* o = reinterpret_cast<float*>(a.out);
+                const int H2 = 2 * a.H, W2 = 2 * a.W;
+#pragma unroll
+                for (int ab = 0; ab < 4; ++ab)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const size_t idx = (((size_t)n * 3 + c) * H2 + 2 * h + (ab >> 1)) * W2 + 2 * w + (ab & 1);
+                        o[idx] = tanhf(f[ab * 3 + c] + __ldg(a.bias + c));
+                    }
+            }
+        }
+    }
+}
+
+template <int EPI, int N>
+__device__ __forceinline__ void flush_stats(const ConvArgs& a, int nb, int lane, float* s1, float* s2) {
+    if constexpr (EPI == CVAE_EPI_STATS) {
+        if (lane < 16) {
+#pragma unroll
+            for (int g = 0; g < N / 16; ++g) {
+                atomicAdd(a.stats + nb * N + g * 16 + lane, (double)s1[g]);
+                atomicAdd(a.stats + a.c_total + nb * N + g * 16 + lane, (double)s2[g]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < N / 16; ++g) s1[g] = s2[g] = 0.f;
+    }
+}
+
+// Barriers of the pipelined kernel (static shared memory).
+static constexpr int kMaxStages = 32;
+struct PipeBars {
+    uint64_t w_full[kMaxStages], w_empty[kMaxStages];
+    uint64_t p_full[2], p_empty[2], acc_full[2], acc_empty[2];
+};
+
+// KS consecutive K steps (same tap, consecutive channel pairs, same ring stage) x TM tiles, fully unrolled:
+// every descriptor is one of three bases plus an immediate (or plus j * cp16, a kernel parameter), so the
+// compiler needs one register -> uniform-register move per base per call instead of several per MMA.
+template <int N, int TM, int KS>
+__device__ __forceinline__ void issue_fixed(uint32_t acc, uint32_t a_lo0, uint32_t b_lo0, uint32_t cp16, uint32_t idesc,
+                                            uint32_t accumulate_first) {
+    const uint32_t a_hi = (128u >> 4) | (1u << 14);  // SBO 128 B, descriptor version 1
+    const uint32_t b_hi = (256u >> 4) | (1u << 14);  // SBO 256 B
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(j * N * 2));
+        const uint32_t a_lo = a_lo0 + (uint32_t)j * cp16;
+#pragma unroll
+        for (int t = 0; t < TM; ++t)
+            umma_bf16(acc + (uint32_t)(t * N), ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(t * 128)), db, idesc,
+                      j == 0 ? accumulate_first : 1u);
+    }
+}
+
+// MMA role of the pipelined kernel, run by ONE elected thread.  The tensor pipe needs max(N/2, 32 + N/4)
+// cycles per 128 x N x 16 MMA (tools/umma_rate.cu) and is starved by anything slower than a handful of
+// uniform-datapath instructions per MMA; every register -> uniform-register move in front of a
+// tcgen05.mma costs tens of cycles.  K steps are therefore issued in fully unrolled groups of KS
+// (KS divides both the channel pairs per tap and the K steps per ring stage).
+template <int N, int KW, int TM, int KS>
+__device__ __forceinline__ void mma_role(const ConvArgs& a, PipeBars& bars, uint32_t tmem_base, uint32_t pbuf16, uint32_t wring_addr,
+                                         int n_items, uint32_t stage_bytes) {
+    const uint32_t idesc = umma_idesc_bf16(N, kMajorK, kMajorK);
+    const uint32_t b_lbo = (128u >> 4) << 16;
+    const uint32_t a_lbo = ((uint32_t)a.plane_stride >> 4) << 16;
+    const uint32_t tap00 = (uint32_t)(a.halo - a.pad * a.PW - a.pad);  // pixel offset of tap (0,0)
+    const uint32_t cp16 = (uint32_t)(2 * a.plane_stride) >> 4;
+    const int G = a.planes >> 1;
+    int logG = 0;
+    while ((1 << logG) < G) ++logG;
+    const int S = a.kpg / a.ksps, groups_per_stage = a.ksps / KS;
+    const int s0 = a.rotate ? (int)(((long)blockIdx.x * S) / gridDim.x) : 0;
+    uint32_t it = 0, p = 0, ws = 0, wphase = 0;
+    bool first_item = true;
+    long long t_acc = 0, t_pl = 0, t_w = 0, t0 = 0, tq = 0;
+    const bool prof = a.dbg != nullptr;
+    if (prof) t0 = clock64();
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ab = it & 1u;
+        if (prof) tq = clock64();
+        mbar_wait(&bars.acc_empty[ab], ((it >> 1) & 1u) ^ 1u, a.fault);
+        if (prof) t_acc += clock64() - tq;
+        tc_fence_after();
+        const uint32_t acc = tmem_base + ab * (uint32_t)(TM * N);
+        uint32_t accumulate = 0;
+        for (int cg = 0; cg < a.ncg; ++cg, ++p) {
+            const uint32_t buf = p & 1u;
+            if (prof) tq = clock64();
+            mbar_wait(&bars.p_full[buf], (p >> 1) & 1u, a.fault);
+            if (prof) t_pl += clock64() - tq;
+            tc_fence_after();
+            const uint32_t a_buf = pbuf16 + ((buf * (uint32_t)a.buf_bytes) >> 4) + tap00;
+            for (int i = 0; i < S; ++i) {
+                int st = s0 + i;
+                if (st >= S) st -= S;
+                if (prof) tq = clock64();
+                if (!a.resident || first_item) mbar_wait(&bars.w_full[ws], wphase, a.fault);
+                if (prof) t_w += clock64() - tq;
+                tc_fence_after();
+                uint32_t b_lo = (((wring_addr + ws * stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                int klin = st * a.ksps;
+                for (int gi = 0; gi < groups_per_stage; ++gi, klin += KS) {
+                    const int tap = klin >> logG, cp0 = klin & (G - 1);
+                    const int ty = tap / KW, tx = tap - ty * KW;
+                    const uint32_t a_lo = (a_buf + (uint32_t)(ty * a.PW + tx) + (uint32_t)cp0 * cp16) | a_lbo;
+                    issue_fixed<N, TM, KS>(acc, a_lo, b_lo, cp16, idesc, accumulate);
+                    accumulate = 1u;
+                    b_lo += (uint32_t)(KS * N * 2);
+                }
+                if (!a.resident) umma_commit(&bars.w_empty[ws]);
+                if (++ws == (uint32_t)a.nstages) { ws = 0; wphase ^= 1u; }
+            }
+            umma_commit(&bars.p_empty[buf]);
+        }
+        umma_commit(&bars.acc_full[ab]);
+        if (a.resident) { ws = 0; wphase = 0; }
+        first_item = false;
+    }
+    if (prof) {
+        unsigned long long* o = a.dbg + (size_t)blockIdx.x * 8;
+        o[0] = (unsigned long long)(clock64() - t0); o[1] = t_acc; o[2] = t_pl; o[3] = t_w; o[4] = it;
+    }
+}
+
+template <int N, int KW, int TM>
+__device__ __forceinline__ void mma_role_ks(const ConvArgs& a, PipeBars& bars, uint32_t tmem_base, uint32_t pbuf16,
+                                            uint32_t wring_addr, int n_items, uint32_t stage_bytes) {
+    if (a.kgroup == 4) mma_role<N, KW, TM, 4>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes);
+    else if (a.kgroup == 2) mma_role<N, KW, TM, 2>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes);
+    else mma_role<N, KW, TM, 1>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes);
+}
+
+// --------------------------------------------------------------------------------------------
+// pipelined kernel
+// --------------------------------------------------------------------------------------------
+static constexpr int kPipeThreads = 320;
+static constexpr int kProducerThreads = 128;  // warps 6-9
+static size_t kStageBytesMax = getenv("CVAE_STAGE_KB") ? (size_t)atoi(getenv("CVAE_STAGE_KB")) * 1024 : 16 * 1024;
+static int kMaxGroupPlanes = getenv("CVAE_GROUP_PLANES") ? atoi(getenv("CVAE_GROUP_PLANES")) : 8;
+static constexpr size_t kDynSmemMax = 216 * 1024;  // 227 KB per CTA minus static shared memory (barriers, statistics scratch)
+
+template <int LOADER, int EPI, int N, int KW>
+__global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ PipeBars bars;
+    uint64_t* const w_full = bars.w_full; uint64_t* const w_empty = bars.w_empty;
+    uint64_t* const p_full = bars.p_full; uint64_t* const p_empty = bars.p_empty;
+    uint64_t* const acc_full = bars.acc_full; uint64_t* const acc_empty = bars.acc_empty;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float stat_scratch[(EPI == CVAE_EPI_STATS) ? 4 * 32 * 17 : 1];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t kstep_bytes = (uint32_t)N * 32u;
+    const uint32_t stage_bytes = (uint32_t)a.ksps * kstep_bytes;
+
+    uint8_t* pbuf = smem;
+    uint8_t* wring = smem + 2 * (size_t)a.buf_bytes;
+
+    if (tid == 0) {
+        for (int s = 0; s < a.nstages; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&p_full[b], kProducerThreads);
+            mbar_init(&p_empty[b], 1);
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);
+        }
+        mbar_fence_init();
+    }
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)(2 * a.tm * N)) ncols <<= 1;
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const int n_items = a.num_chunks * a.n_blocks;
+    const int spg = a.kpg / a.ksps;  // weight stages per channel group
+
+    if (warp < 4) {
+        // ================================ epilogue ================================================
+        float s1[(EPI == CVAE_EPI_STATS) ? N / 16 : 1], s2[(EPI == CVAE_EPI_STATS) ? N / 16 : 1];
+#pragma unroll
+        for (int g = 0; g < ((EPI == CVAE_EPI_STATS) ? N / 16 : 1); ++g) s1[g] = s2[g] = 0.f;
+        int cur_nb = -1;
+        uint32_t it = 0;
+        long long t_epi = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int nb = item / a.num_chunks, chunk = item - nb * a.num_chunks;
+            if (nb != cur_nb) {
+                if (cur_nb >= 0) flush_stats<EPI, N>(a, cur_nb, lane, s1, s2);
+                cur_nb = nb;
+            }
+            const uint32_t ab = it & 1u;
+            mbar_wait(&acc_full[ab], (it >> 1) & 1u, a.fault);
+            tc_fence_after();
+            const long long te = clock64();
+            const int v0 = a.pad * a.PW + chunk * a.tm * 128;
+            for (int t = 0; t < a.tm && !(a.dbg_flags & 1); ++t)
+                epilogue_tile<EPI, N>(a, tmem_base + ab * (uint32_t)(a.tm * N) + (uint32_t)(t * N), v0 + t * 128, nb, warp,
+                                      lane, s1, s2, stat_scratch);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+            t_epi += clock64() - te;
+        }
+        if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 8 + 7] = t_epi;
+        if (cur_nb >= 0) flush_stats<EPI, N>(a, cur_nb, lane, s1, s2);
+    } else if (warp == kPipeThreads / 32 - 1) {
+        // ================================ MMA issuer (highest warp id: the scheduler favours it) ==============================================
+        if (elect_one()) {
+            const uint32_t pbuf16 = (smem_u32(pbuf) & 0x3FFFFu) >> 4, wring_addr = smem_u32(wring);
+            switch (a.tm) {
+                case 1: mma_role_ks<N, KW, 1>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes); break;
+                case 2: mma_role_ks<N, KW, 2>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes); break;
+                case 3: mma_role_ks<N, KW, 3>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes); break;
+                case 4: mma_role_ks<N, KW, 4>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes); break;
+                case 6: mma_role_ks<N, KW, 6>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes); break;
+                default: mma_role_ks<N, KW, 8>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes); break;
+            }
+        }
+        __syncwarp();
+    } else if (warp == kPipeThreads / 32 - 2) {
+        // ================================ weight producer =========================================
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(a.wpack);
+        const int cpairs_total = a.ksteps / (a.KW * a.KW);  // GENERIC only
+        const int G = a.planes >> 1;
+        const int s0w = a.rotate ? (int)(((long)blockIdx.x * spg) / gridDim.x) : 0;
+        uint32_t ws = 0, wphase = 0;
+        bool first_item = true;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            if (a.resident && !first_item) break;
+            const int nb = item / a.num_chunks;
+            const int col0 = nb * N;
+            const int pb = col0 / a.nb_pack, sub = col0 - pb * a.nb_pack;
+            for (int cg = 0; cg < a.ncg; ++cg) {
+                for (int i = 0; i < spg; ++i) {
+                    int st = s0w + i;
+                    if (st >= spg) st -= spg;
+                    if (!a.resident) mbar_wait(&w_empty[ws], wphase ^ 1u, a.fault);
+                    int kglob;  // first global K step of this stage
+                    if (a.ncg == 1) kglob = st * a.ksps;
+                    else {
+                        const int kl = st * a.ksps, tap = kl / G, j0 = kl - tap * G;
+                        kglob = tap * cpairs_total + cg * G + j0;
+                    }
+                    if (elect_one()) {
+                        mbar_expect_tx(&w_full[ws], stage_bytes);
+                        uint8_t* dst = wring + (size_t)ws * stage_bytes;
+                        if (N == a.nb_pack) {
+                            bulk_g2s(dst, wbase + ((size_t)pb * a.ksteps + kglob) * a.nb_pack * 32, stage_bytes, &w_full[ws]);
+                        } else {
+                            for (int ks = 0; ks < a.ksps; ++ks)
+                                bulk_g2s(dst + (size_t)ks * kstep_bytes,
+                                         wbase + (((size_t)pb * a.ksteps + kglob + ks) * a.nb_pack + sub) * 32, kstep_bytes,
+                                         &w_full[ws]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++ws == (uint32_t)a.nstages) { ws = 0; wphase ^= 1u; }
+                }
+            }
+            first_item = false;
+        }
+    } else {
+        // ================================ plane producers =========================================
+        const int ptid = tid - 128;  // warps 4-7
+        uint32_t p = 0;
+        bool alive = true;
+        long long t_fill = 0, t_pe = 0, tq;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int nb = item / a.num_chunks, chunk = item - nb * a.num_chunks;
+            const int v0 = a.pad * a.PW + chunk * a.tm * 128;
+            for (int cg = 0; cg < a.ncg; ++cg, ++p) {
+                const uint32_t buf = p & 1u;
+                tq = clock64();
+                if (alive) alive = mbar_wait(&p_empty[buf], ((p >> 1) & 1u) ^ 1u, a.fault);
+                t_pe += clock64() - tq;
+                tq = clock64();
+                if (!(a.dbg_flags & 2) || p < 2)
+                fill_planes_async<LOADER>(a.ps, a.dPW, a.dIH, pbuf + (size_t)buf * a.buf_bytes, a.plane_stride, v0 - a.halo, a.L,
+                                          cg * a.planes, a.planes, ptid, kProducerThreads);
+                cp_async_wait_all();
+                fence_proxy_async();
+                mbar_arrive(&p_full[buf]);
+                t_fill += clock64() - tq;
+            }
+        }
+        if (a.dbg && ptid == 0) {
+            unsigned long long* o = a.dbg + (size_t)blockIdx.x * 8;
+            o[5] = t_fill;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem_base, ncols);
+}
+
+// --------------------------------------------------------------------------------------------
+// phase-sequential kernel (fp32 NCHW loaders): load planes -> MMA -> epilogue per pass
+// --------------------------------------------------------------------------------------------
+static constexpr int kThreads = 192;  // warps 0-3: loader + epilogue, 4: weight producer, 5: MMA
+
 template <int LOADER, int EPI, int N>
 __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int kMaxStages = 6;
-    __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc;
+    constexpr int kSeqStages = 6;
+    __shared__ uint64_t bar_full[kSeqStages], bar_empty[kSeqStages], bar_acc;
     __shared__ uint32_t tmem_slot;
     __shared__ float stat_scratch[(EPI == CVAE_EPI_STATS) ? 4 * 32 * 17 : 1];
 
@@ -62,7 +505,6 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
     uint8_t* wring = smem + (((size_t)a.planes * a.plane_stride + 1023) & ~(size_t)1023);
     uint2* ktab = reinterpret_cast<uint2*>(wring + (size_t)a.nstages * stage_bytes);
 
-    // ---- one-time setup -------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < a.nstages; ++s) {
             mbar_init(&bar_full[s], 1);
@@ -74,30 +516,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
     uint32_t ncols = 32;
     while (ncols < (uint32_t)(a.tm * N)) ncols <<= 1;
     if (warp == 0) tmem_alloc(&tmem_slot, ncols);
-    for (int i = tid; i < a.ksteps; i += kThreads) {
-        uint2 e;
-        if (a.ktab_mode == CVAE_KTAB_GENERIC) {
-            const int cpairs = a.planes >> 1;
-            const int tap = i / cpairs, cp = i - tap * cpairs;
-            const int dy = tap / a.KW - a.pad, dx = tap % a.KW - a.pad;
-            e.x = (uint32_t)(a.halo + dy * a.PW + dx) * 16u + (uint32_t)cp * 2u * a.plane_stride;
-            e.y = (uint32_t)a.plane_stride;
-        } else {  // PAIR8: 5x5 taps of an 8-channel source, two taps per K step
-            if (i < 10) {
-                const int ky = i >> 1, kx = (i & 1) * 2;
-                e.x = (uint32_t)(a.halo + (ky - 2) * a.PW + (kx - 2)) * 16u;
-                e.y = 16u;
-            } else if (i < 12) {
-                const int ky = (i - 10) * 2;
-                e.x = (uint32_t)(a.halo + (ky - 2) * a.PW + 2) * 16u;
-                e.y = (uint32_t)a.PW * 16u;
-            } else {
-                e.x = (uint32_t)(a.halo + 2 * a.PW + 2) * 16u;
-                e.y = 16u;
-            }
-        }
-        ktab[i] = e;
-    }
+    for (int i = tid; i < a.ksteps; i += kThreads) ktab[i] = ktab_entry(a, i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -128,8 +547,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
                     alive = mbar_wait(&bar_empty[ring_stage], ring_phase ^ 1, a.fault);
                     mbar_expect_tx(&bar_full[ring_stage], stage_bytes);
                     bulk_g2s(wring + (size_t)ring_stage * stage_bytes,
-                             reinterpret_cast<const uint8_t*>(wsrc) + (size_t)st * stage_bytes,
-                             stage_bytes, &bar_full[ring_stage]);
+                             reinterpret_cast<const uint8_t*>(wsrc) + (size_t)st * stage_bytes, stage_bytes,
+                             &bar_full[ring_stage]);
                     if (++ring_stage == (uint32_t)a.nstages) { ring_stage = 0; ring_phase ^= 1; }
                 }
             }
@@ -142,9 +561,6 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
                     alive = mbar_wait(&bar_full[ring_stage], ring_phase, a.fault);
                     tc_fence_after();
                     const uint32_t wb = wring_addr + ring_stage * stage_bytes;
-                    // One elected thread feeds the tensor pipe, so the issue loop must stay at a handful
-                    // of instructions per MMA: descriptors are built once per K step and the tile index
-                    // only bumps the 16-byte-granular start-address field (2048 B per 128-pixel tile).
                     for (int ks = 0; ks < a.ksps; ++ks) {
                         const int kidx = st * a.ksps + ks;
                         const uint2 e = ktab[kidx];
@@ -155,7 +571,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
 #pragma unroll 4
                         for (int t = 0; t < a.tm; ++t) {
                             umma_bf16(tcol, da, db, idesc, accumulate);
-                            da += 128;   // (2048 >> 4)
+                            da += 128;
                             tcol += N;
                         }
                     }
@@ -166,113 +582,10 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
             }
             __syncwarp();
         } else {
-            // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32) = rows of every tile -----------
             mbar_wait(&bar_acc, acc_phase, a.fault);
             tc_fence_after();
-            for (int t = 0; t < a.tm; ++t) {
-                const int v = v0 + t * 128 + warp * 32 + lane;
-                int vrow = v / a.PW;
-                int vcol = v - vrow * a.PW;
-                int n = vrow / a.IH;
-                int r = vrow - n * a.IH;
-                const bool valid = (vcol < a.W) && (r >= a.pad) && (n < a.B);
-                const int h = r - a.pad, w = vcol;
-                const size_t pix = ((size_t)n * a.H + h) * a.W + w;
-#pragma unroll
-                for (int g = 0; g < N / 16; ++g) {
-                    uint32_t raw[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * N + g * 16), raw);
-                    tmem_wait_ld();
-                    float f[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(raw[i]);
-                    const int c0 = nb * N + g * 16;  // first global output column of this group
-
-                    if constexpr (EPI == CVAE_EPI_STATS) {
-                        uint32_t p[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-                        float* sc = stat_scratch + warp * 32 * 17;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            sc[lane * 17 + 2 * i] = valid ? bf16_lo(p[i]) : 0.f;
-                            sc[lane * 17 + 2 * i + 1] = valid ? bf16_hi(p[i]) : 0.f;
-                        }
-                        __syncwarp();
-                        const int col = lane & 15, half = lane >> 4;
-                        float sa = 0.f, sb = 0.f;
-#pragma unroll
-                        for (int rr = 0; rr < 16; ++rr) {
-                            const float x = sc[(half * 16 + rr) * 17 + col];
-                            sa += x;
-                            sb += x * x;
-                        }
-                        sa += __shfl_xor_sync(0xffffffffu, sa, 16);
-                        sb += __shfl_xor_sync(0xffffffffu, sb, 16);
-                        s1[g] += sa;
-                        s2[g] += sb;
-                        __syncwarp();
-                        if (valid) {
-                            uint4* o = reinterpret_cast<uint4*>(
-                                reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.c_total + c0);
-                            o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                            o[1] = make_uint4(p[4], p[5], p[6], p[7]);
-                        }
-                    } else if constexpr (EPI == CVAE_EPI_BIAS_RELU || EPI == CVAE_EPI_PLAIN ||
-                                         EPI == CVAE_EPI_MASK) {
-                        if (valid) {
-                            if constexpr (EPI == CVAE_EPI_BIAS_RELU) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i] + __ldg(a.bias + c0 + i), 0.f);
-                            }
-                            if constexpr (EPI == CVAE_EPI_MASK) {
-                                const uint4* m = reinterpret_cast<const uint4*>(a.act + pix * a.c_total + c0);
-                                const uint4 m0 = __ldg(m), m1 = __ldg(m + 1);
-                                const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    if (!(bf16_lo(mm[i]) > 0.f)) f[2 * i] = 0.f;
-                                    if (!(bf16_hi(mm[i]) > 0.f)) f[2 * i + 1] = 0.f;
-                                }
-                            }
-                            uint32_t p[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-                            uint4* o = reinterpret_cast<uint4*>(
-                                reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.c_total + c0);
-                            o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                            o[1] = make_uint4(p[4], p[5], p[6], p[7]);
-                        }
-                    } else if constexpr (EPI == CVAE_EPI_PHASE_BIAS_RELU) {
-                        if (valid) {
-                            const int cout = a.c_total >> 2;
-                            const int ab = c0 / cout, co = c0 - ab * cout;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i] + __ldg(a.bias + co + i), 0.f);
-                            uint32_t p[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) p[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-                            const size_t opix = ((size_t)n * 2 * a.H + 2 * h + (ab >> 1)) * (2 * a.W) + 2 * w + (ab & 1);
-                            uint4* o = reinterpret_cast<uint4*>(
-                                reinterpret_cast<__nv_bfloat16*>(a.out) + opix * cout + co);
-                            o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                            o[1] = make_uint4(p[4], p[5], p[6], p[7]);
-                        }
-                    } else {  // CVAE_EPI_PHASE_BIAS_TANH: 12 of the 16 columns are (a,b,c)
-                        if (valid) {
-                            float* o = reinterpret_cast<float*>(a.out);
-                            const int H2 = 2 * a.H, W2 = 2 * a.W;
-#pragma unroll
-                            for (int ab = 0; ab < 4; ++ab)
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) {
-                                    const size_t idx = (((size_t)n * 3 + c) * H2 + 2 * h + (ab >> 1)) * W2 + 2 * w + (ab & 1);
-                                    o[idx] = tanhf(f[ab * 3 + c] + __ldg(a.bias + c));
-                                }
-                        }
-                    }
-                }
-            }
+            for (int t = 0; t < a.tm; ++t)
+                epilogue_tile<EPI, N>(a, tmem_base + (uint32_t)(t * N), v0 + t * 128, nb, warp, lane, s1, s2, stat_scratch);
             acc_phase ^= 1;
         }
         tc_fence_before();
@@ -280,23 +593,18 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
         tc_fence_after();
     }
 
-    if constexpr (EPI == CVAE_EPI_STATS) {
-        if (warp < 4 && lane < 16) {
-#pragma unroll
-            for (int g = 0; g < N / 16; ++g) {
-                atomicAdd(a.stats + nb * N + g * 16 + lane, (double)s1[g]);
-                atomicAdd(a.stats + a.c_total + nb * N + g * 16 + lane, (double)s2[g]);
-            }
-        }
-    }
+    if (warp < 4) flush_stats<EPI, N>(a, nb, lane, s1, s2);
     if (warp == 0) tmem_free(tmem_base, ncols);
 }
 
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
+static const bool g_debug = getenv("CVAE_DEBUG") != nullptr;
+static unsigned long long* g_dbg_counters = nullptr;
+
 template <int LOADER, int EPI, int N>
-static int launch(const ConvArgs& a, size_t smem, cudaStream_t stream) {
+static int launch_seq(const ConvArgs& a, size_t smem, cudaStream_t stream) {
     auto kern = conv_gemm_kernel<LOADER, EPI, N>;
     static thread_local size_t configured = 0;
     if (smem > configured) {
@@ -305,20 +613,38 @@ static int launch(const ConvArgs& a, size_t smem, cudaStream_t stream) {
     }
     uint32_t ncols = 32;
     while (ncols < (uint32_t)(a.tm * N)) ncols <<= 1;
-    int per_sm = (int)((228 * 1024) / (smem + 2048));          // shared-memory limit (1 KB static + 1 KB reserved per CTA)
-    if (per_sm > (int)(512 / ncols)) per_sm = (int)(512 / ncols);  // TMEM limit
+    int per_sm = (int)((228 * 1024) / (smem + 2048));
+    if (per_sm > (int)(512 / ncols)) per_sm = (int)(512 / ncols);
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     int gx = sm_count() * per_sm / a.n_blocks;
     if (gx < 1) gx = 1;
     if (gx > a.num_chunks) gx = a.num_chunks;
     dim3 grid(gx, a.n_blocks);
-    static const bool debug = getenv("CVAE_DEBUG") != nullptr;
-    if (debug)
-        fprintf(stderr, "conv_gemm<L%d,E%d,N%d> B=%d %dx%d planes=%d ksteps=%d ksps=%d stages=%d tm=%d chunks=%d smem=%zu "
-                        "cols=%u per_sm=%d grid=(%d,%d)\n", LOADER, EPI, N, a.B, a.H, a.W, a.planes, a.ksteps, a.ksps,
-                a.nstages, a.tm, a.num_chunks, smem, ncols, per_sm, gx, a.n_blocks);
     kern<<<grid, kThreads, smem, stream>>>(a);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+template <int LOADER, int EPI, int N, int KW>
+static int launch_pipe(const ConvArgs& a, size_t smem, cudaStream_t stream) {
+    auto kern = conv_pipe_kernel<LOADER, EPI, N, KW>;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        CVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int items = a.num_chunks * a.n_blocks;
+    int gx = sm_count();
+    if (gx > items) gx = items;
+    // balance: every CTA gets the same number of items where possible
+    const int waves = (items + gx - 1) / gx;
+    gx = (items + waves - 1) / waves;
+    if (g_debug)
+        fprintf(stderr, "conv_pipe<L%d,E%d,N%d> B=%d %dx%d planes=%dx%d ksteps=%d kpg=%d ksps=%d stages=%d%s tm=%d chunks=%d "
+                        "nblk=%d smem=%zu grid=%d\n", LOADER, EPI, N, a.B, a.H, a.W, a.planes, a.ncg, a.ksteps, a.kpg, a.ksps,
+                a.nstages, a.resident ? "(resident)" : "", a.tm, a.num_chunks, a.n_blocks, smem, gx);
+    kern<<<gx, kPipeThreads, smem, stream>>>(a);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -327,9 +653,56 @@ static int launch(const ConvArgs& a, size_t smem, cudaStream_t stream) {
 
 using namespace cvae;
 
+// Profiling aid: when set, every pipelined conv CTA writes 8 cycle counters (MMA thread: total, wait for
+// accumulator, planes, weights, items; producers: fill, wait; epilogue) to buf[blockIdx.x * 8 ..].
+extern "C" void cvae_conv_debug_counters(void* device_buf) { g_dbg_counters = (unsigned long long*)device_buf; }
+
 extern "C" int cvae_conv_ksteps(int ksize, int src_channels, int ktab) {
     if (ktab == CVAE_KTAB_PAIR8) return 13;
     return ksize * ksize * (src_channels / 16);
+}
+
+static int conv_sequential(const cvae_conv_desc* d, ConvArgs& a, cudaStream_t stream) {
+    const int N = a.nb_pack;
+    a.n_blocks = d->n_total / N;
+    a.planes = d->src_channels / 8;
+    a.ncg = 1;
+    a.kpg = a.ksteps;
+    if (d->ktab == CVAE_KTAB_PAIR8) a.ksps = 13;
+    else {
+        a.ksps = d->src_channels / 16;  // one tap
+        while (a.ksps * N * 32 > 8 * 1024 && a.ksps % 2 == 0) a.ksps /= 2;
+    }
+    CVAE_REQUIRE(a.ksteps % a.ksps == 0, CVAE_EINVAL, "conv_gemm: internal stage split");
+    const size_t stage_bytes = (size_t)a.ksps * N * 32;
+    const long total_v = (long)a.B * a.IH * a.PW - (long)a.pad * a.PW;
+    const int total_tiles = (int)((total_v + 127) / 128);
+    auto smem_for = [&](int tm, int nstages) {
+        const size_t L = (size_t)tm * 128 + 2 * a.halo + 8;
+        return (((size_t)a.planes * L * 16 + 1023) & ~(size_t)1023) + nstages * stage_bytes + (size_t)a.ksteps * 8 + 64;
+    };
+    int tm = d->tm > 0 ? d->tm : (256 / N > 0 ? 256 / N : 1);
+    if (tm > 8) tm = 8;
+    if (tm > total_tiles) tm = total_tiles;
+    a.nstages = 3;
+    const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024;
+    if (d->tm <= 0)
+        while (tm > 1 && smem_for(tm, 3) > two_per_sm) --tm;
+    while (tm > 1 && (smem_for(tm, a.nstages) > one_per_sm || tm * N > 512)) --tm;
+    CVAE_REQUIRE(smem_for(tm, a.nstages) <= one_per_sm && tm * N <= 512, CVAE_EINVAL, "conv_gemm: shape does not fit shared memory");
+    a.tm = tm;
+    a.L = tm * 128 + 2 * a.halo + 8;
+    a.plane_stride = a.L * 16;
+    const size_t smem = smem_for(tm, a.nstages);
+    a.num_chunks = (total_tiles + a.tm - 1) / a.tm;
+    CVAE_REQUIRE((size_t)a.planes * a.plane_stride < (1u << 18), CVAE_EINVAL, "conv_gemm: planes exceed descriptor range");
+#define CVAE_CASE(L_, E_, N_) \
+    if (d->loader == (L_) && d->epilogue == (E_) && N == (N_)) return launch_seq<L_, E_, N_>(a, smem, stream);
+    CVAE_CASE(CVAE_LOAD_NCHW3, CVAE_EPI_STATS, 32)
+    CVAE_CASE(CVAE_LOAD_S2D_NCHW3_DTANH, CVAE_EPI_MASK, 32)
+#undef CVAE_CASE
+    set_error("conv_gemm: no sequential kernel for loader %d epilogue %d N %d", d->loader, d->epilogue, N);
+    return CVAE_EINVAL;
 }
 
 extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
@@ -347,10 +720,9 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     ConvArgs a{};
     a.B = d->batch; a.H = d->height; a.W = d->width; a.KW = d->ksize; a.pad = d->ksize / 2;
     a.PW = a.W + a.pad; a.IH = a.H + a.pad;
-    a.planes = d->src_channels / 8;
-    const int N = d->n_total < 128 ? d->n_total : 128;
-    CVAE_REQUIRE(d->n_total % N == 0, CVAE_EINVAL, "conv_gemm: n_total %d not a multiple of %d", d->n_total, N);
-    a.n_blocks = d->n_total / N;
+    a.dPW = make_fastdiv(a.PW); a.dIH = make_fastdiv(a.IH);
+    a.nb_pack = d->n_total < 128 ? d->n_total : 128;
+    CVAE_REQUIRE(d->n_total % a.nb_pack == 0, CVAE_EINVAL, "conv_gemm: n_total %d not a multiple of %d", d->n_total, a.nb_pack);
     a.c_total = d->n_total;
     a.ksteps = cvae_conv_ksteps(d->ksize, d->src_channels, d->ktab);
     a.ktab_mode = d->ktab;
@@ -358,62 +730,99 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     a.wpack = (const __nv_bfloat16*)d->wpack; a.out = d->out;
     a.bias = d->bias; a.act = (const __nv_bfloat16*)d->act; a.stats = d->stats;
     a.fault = fault_flag();
+    a.dbg = g_dbg_counters;
+    a.dbg_flags = getenv("CVAE_DBG_FLAGS") ? atoi(getenv("CVAE_DBG_FLAGS")) : 0;
     CVAE_REQUIRE(a.fault != nullptr, CVAE_ECUDA, "conv_gemm: fault flag unavailable");
-    a.ps = PlaneSrc{a.B, a.H, a.W, a.pad, a.PW, a.IH, a.planes,
+    const int all_planes = d->src_channels / 8;
+    a.ps = PlaneSrc{a.B, a.H, a.W, a.pad, a.PW, a.IH, all_planes,
                     (d->loader == CVAE_LOAD_S2D) ? d->src_channels / 4 : d->src_channels, 0, d->src, d->src2};
 
-    // Tiling policy.  Phases inside a CTA are sequential (load planes -> MMA -> epilogue), so overlap
-    // comes from co-resident CTAs: aim for >= 2 CTAs per SM (<= 112 KB of shared memory and <= 256
-    // TMEM columns each), with as many 128-pixel tiles per pass as fit -- every tile of a pass reuses
-    // the same weight stage, so `tm` divides the L2 -> SM weight traffic.
-    if (d->ktab == CVAE_KTAB_PAIR8) a.ksps = 13;
-    else {
-        a.ksps = d->src_channels / 16;                       // one tap
-        while (a.ksps * N * 32 > 8 * 1024 && a.ksps % 2 == 0) a.ksps /= 2;
-    }
-    CVAE_REQUIRE(a.ksteps % a.ksps == 0, CVAE_EINVAL, "conv_gemm: internal stage split");
-    const size_t stage_bytes = (size_t)a.ksps * N * 32;
+    if (d->loader == CVAE_LOAD_NCHW3 || d->loader == CVAE_LOAD_S2D_NCHW3_DTANH) return conv_sequential(d, a, stream);
 
+    // ---- tiling policy of the pipelined kernel -----------------------------------------------------
     const long total_v = (long)a.B * a.IH * a.PW - (long)a.pad * a.PW;  // pixels from first to last valid row
     const int total_tiles = (int)((total_v + 127) / 128);
-    auto smem_for = [&](int tm, int nstages) {
-        const size_t L = (size_t)tm * 128 + 2 * a.halo + 8;
-        return (((size_t)a.planes * L * 16 + 1023) & ~(size_t)1023) + nstages * stage_bytes + (size_t)a.ksteps * 8 + 64;
-    };
-    int tm = d->tm > 0 ? d->tm : (256 / N > 0 ? 256 / N : 1);
-    if (tm > 8) tm = 8;
-    if (tm > total_tiles) tm = total_tiles;
-    a.nstages = 3;
-    const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024;
-    if (d->tm <= 0) {
-        while (tm > 1 && smem_for(tm, 3) > two_per_sm) --tm;
-        if (smem_for(tm, 3) > two_per_sm && smem_for(tm, 2) <= two_per_sm) a.nstages = 2;
+    const int sms = sm_count();
+    // channel groups of <= 128 channels (16 planes)
+    a.planes = all_planes;
+    a.ncg = 1;
+    while (a.planes > kMaxGroupPlanes && a.planes % 4 == 0) { a.planes /= 2; a.ncg *= 2; }
+    if (d->ktab == CVAE_KTAB_PAIR8) a.kpg = 13;
+    else a.kpg = d->ksize * d->ksize * (a.planes / 2);
+
+    // Work decomposition.  N block = the packed block (<= 128 columns; narrower blocks only cost shared-memory
+    // bandwidth: an SS-mode MMA reads 4 KB of A regardless of N).  tm (tiles per pass, sharing every weight
+    // stage) from a small cost model fitted to tools/conv_bench.py sweeps on B200: per CTA
+    //   max(MMA cycles, weight-stream cycles at ~17 B/clk/SM of shared L2 reads) + per-item pipeline fill.
+    int N = d->n_block > 0 ? d->n_block : a.nb_pack;
+    int tm = d->tm;
+    if (tm <= 0) {
+        double best = 1e30;
+        tm = 1;
+        const double mma_cyc = (N / 2.0 > 32.0 + N / 4.0 ? N / 2.0 : 32.0 + N / 4.0) * 1.3;
+        for (int t : {1, 2, 3, 4, 6, 8}) {
+            if (2 * t * N > 512 || (t > 1 && t > total_tiles)) continue;
+            const size_t L = (size_t)t * 128 + 2 * a.halo + 8;
+            const size_t buf = ((size_t)a.planes * L * 16 + 1023) & ~(size_t)1023;
+            if (2 * buf + 32 * 1024 > kDynSmemMax) continue;
+            const long chunks = (total_tiles + t - 1) / t;
+            const long items = chunks * (d->n_total / N);
+            long gx = items < sms ? items : sms;
+            const long per_cta = (items + gx - 1) / gx;
+            const double t_mma = (double)per_cta * t * a.ksteps * mma_cyc;
+            double bw = 2500.0 / (double)gx;
+            if (bw > 40.0) bw = 40.0;
+            const double t_w = (double)per_cta * a.ksteps * N * 32.0 / bw;
+            const double est = (t_mma > t_w ? t_mma : t_w) + (double)per_cta * (2500.0 + 600.0 * t);
+            if (est < best) { best = est; tm = t; }
+        }
     }
-    while (tm > 1 && (smem_for(tm, a.nstages) > one_per_sm || tm * N > 512)) --tm;
-    CVAE_REQUIRE(smem_for(tm, a.nstages) <= one_per_sm && tm * N <= 512, CVAE_EINVAL, "conv_gemm: shape does not fit shared memory");
+    CVAE_REQUIRE(N >= 16 && N <= 128 && a.nb_pack % N == 0, CVAE_EINVAL, "conv_gemm: n_block %d", N);
+    if (tm > total_tiles) tm = total_tiles;
+    while (tm > 1 && 2 * tm * N > 512) --tm;   // two accumulator sets must fit the 512 TMEM columns
+    if (tm == 5) tm = 4;
+    if (tm == 7) tm = 6;
+    CVAE_REQUIRE(d->ktab == CVAE_KTAB_GENERIC, CVAE_EINVAL, "conv_gemm: the pipelined kernel needs the generic K order");
+    CVAE_REQUIRE(tm >= 1 && 2 * tm * N <= 512, CVAE_EINVAL, "conv_gemm: tm %d x n_block %d exceeds tensor memory", tm, N);
+    a.n_blocks = d->n_total / N;
     a.tm = tm;
     a.L = tm * 128 + 2 * a.halo + 8;
     a.plane_stride = a.L * 16;
-    const size_t smem = smem_for(tm, a.nstages);
-    a.num_chunks = (total_tiles + a.tm - 1) / a.tm;
-    CVAE_REQUIRE((size_t)a.planes * a.plane_stride < (1u << 18), CVAE_EINVAL, "conv_gemm: planes exceed descriptor range");
+    a.buf_bytes = (int)((((size_t)a.planes * a.plane_stride) + 1023) & ~(size_t)1023);
+    a.num_chunks = (total_tiles + tm - 1) / tm;
+    CVAE_REQUIRE((size_t)2 * a.buf_bytes < (1u << 18), CVAE_EINVAL, "conv_gemm: planes exceed descriptor range");
 
-#define CVAE_CASE(L_, E_, N_)                                                     \
-    if (d->loader == (L_) && d->epilogue == (E_) && N == (N_))                    \
-        return launch<L_, E_, N_>(a, smem, stream);
-    CVAE_CASE(CVAE_LOAD_NCHW3, CVAE_EPI_STATS, 32)
-    CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_STATS, 64)
-    CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_STATS, 128)
-    CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_BIAS_RELU, 128)
-    CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_PHASE_BIAS_RELU, 128)
-    CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_PHASE_BIAS_TANH, 16)
-    CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_PLAIN, 32)
-    CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_PLAIN, 64)
-    CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_PLAIN, 128)
-    CVAE_CASE(CVAE_LOAD_S2D, CVAE_EPI_MASK, 128)
-    CVAE_CASE(CVAE_LOAD_S2D, CVAE_EPI_MASK, 64)
-    CVAE_CASE(CVAE_LOAD_S2D, CVAE_EPI_MASK, 32)
-    CVAE_CASE(CVAE_LOAD_S2D_NCHW3_DTANH, CVAE_EPI_MASK, 32)
+    // weight stages: ~4-8 KB each, as many as fit; resident when the whole matrix fits
+    const int G = a.planes / 2;
+    const int run = (a.ncg == 1 || d->ktab == CVAE_KTAB_PAIR8) ? a.kpg : G;  // contiguous K steps in global memory
+    CVAE_REQUIRE((G & (G - 1)) == 0, CVAE_EINVAL, "conv_gemm: channel pairs per group must be a power of two");
+    a.rotate = getenv("CVAE_NO_ROTATE") ? 0 : 1;
+    a.kgroup = (G % 4 == 0) ? 4 : (G % 2 == 0 ? 2 : 1);
+    while (a.kgroup > 1 && (size_t)a.kgroup * N * 32 > kStageBytesMax) a.kgroup /= 2;
+    a.ksps = a.kgroup;
+    for (int c = a.kgroup; c <= run; c += a.kgroup)
+        if (run % c == 0 && a.kpg % c == 0 && (size_t)c * N * 32 <= kStageBytesMax) a.ksps = c;
+    const size_t stage_bytes = (size_t)a.ksps * N * 32;
+    const long budget = (long)kDynSmemMax - 2 * (long)a.buf_bytes - (long)a.kpg * 8 - 64;
+    CVAE_REQUIRE(budget >= (long)(2 * stage_bytes), CVAE_EINVAL, "conv_gemm: shape does not fit shared memory");
+    int nstages = (int)(budget / (long)stage_bytes);
+    if (nstages > kMaxStages) nstages = kMaxStages;
+    const int stages_total = a.ncg * (a.kpg / a.ksps);
+    a.resident = (a.n_blocks == 1 && stages_total <= nstages) ? 1 : 0;
+    if (a.resident) nstages = stages_total;
+    a.nstages = nstages;
+    const size_t smem = 2 * (size_t)a.buf_bytes + (size_t)nstages * stage_bytes + (size_t)a.kpg * 8 + 64;
+
+#define CVAE_CASE(L_, E_, N_, K_) \
+    if (d->loader == (L_) && d->epilogue == (E_) && N == (N_) && d->ksize == (K_)) return launch_pipe<L_, E_, N_, K_>(a, smem, stream);
+#define CVAE_CASES(L_, E_, K_) CVAE_CASE(L_, E_, 16, K_) CVAE_CASE(L_, E_, 32, K_) CVAE_CASE(L_, E_, 64, K_) CVAE_CASE(L_, E_, 128, K_)
+    CVAE_CASES(CVAE_LOAD_NHWC, CVAE_EPI_STATS, 5)
+    CVAE_CASES(CVAE_LOAD_NHWC, CVAE_EPI_BIAS_RELU, 5)
+    CVAE_CASES(CVAE_LOAD_NHWC, CVAE_EPI_PHASE_BIAS_RELU, 3)
+    CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_PHASE_BIAS_TANH, 16, 3)
+    CVAE_CASES(CVAE_LOAD_NHWC, CVAE_EPI_PLAIN, 5)
+    CVAE_CASES(CVAE_LOAD_S2D, CVAE_EPI_MASK, 3)
+#undef CVAE_CASES
 #undef CVAE_CASE
     set_error("conv_gemm: no kernel for loader %d epilogue %d N %d", d->loader, d->epilogue, N);
     return CVAE_EINVAL;

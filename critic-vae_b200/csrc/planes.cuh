@@ -7,6 +7,7 @@
 // is the shared zero padding of the convolution.
 #pragma once
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace cvae {
 
@@ -18,6 +19,90 @@ struct PlaneSrc {
     const void* src;
     const void* src2;
 };
+
+// Division by a run-time constant via multiply-high (exact for 0 <= n < 2^31).
+struct FastDiv {
+    uint32_t d, mul, shift;
+};
+static inline FastDiv make_fastdiv(int d) {
+    FastDiv f{(uint32_t)d, 0u, 0u};
+    if (d > 1) {
+        int lg = 0;
+        while ((1LL << lg) < d) ++lg;
+        const int p = 31 + lg;
+        f.mul = (uint32_t)(((1ULL << p) + (uint64_t)d - 1) / (uint64_t)d);
+        f.shift = (uint32_t)(p - 32);
+    }
+    return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+    return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shift);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// Asynchronous plane fill (cp.async, 16 bytes per copy, zero-fill for padding) for the bf16 loaders.
+// Planes [q_first, q_first + nplanes) of the source are written to planes 0.. of the buffer.
+// Lanes are grouped so that `g` consecutive lanes copy consecutive 16-byte chunks of one pixel
+// (coalesced global reads); every lane decodes its pixel once per iteration.
+template <int LOADER>
+__device__ __forceinline__ void fill_planes_async(const PlaneSrc& a, const FastDiv& dPW, const FastDiv& dIH, uint8_t* planes,
+                                                  int plane_stride, int v_first, int count, int q_first, int nplanes,
+                                                  int tid, int nthreads) {
+    static_assert(LOADER == CVAE_LOAD_NHWC || LOADER == CVAE_LOAD_S2D, "cp.async fill needs a bf16 source");
+    int g = 1;
+    while (g < 8 && g * 2 <= nplanes) g <<= 1;          // lanes per pixel: 1, 2, 4 or 8
+    const int sub = tid & (g - 1);
+    const int workers = nthreads / g;                    // pixel walkers
+    const int wid = tid / g;
+    // every walker owns a contiguous run of pixel slots and decodes (image, row, column) once, then steps
+    const int per = (count + workers - 1) / workers;
+    int j = wid * per;
+    const int j_end = min(j + per, count);
+    if (j >= j_end) return;
+    const uint32_t base = smem_u32(planes);
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.src);
+    const int cq = a.src_c >> 3;                         // S2D: 16-byte chunks per raw pixel
+    int v = v_first + j;
+    int n, r, vcol;
+    if (v < 0) {                                         // before the first image: pure padding
+        n = -1; r = 0; vcol = 0;
+    } else {
+        const uint32_t vrow = fast_div((uint32_t)v, dPW);
+        vcol = (int)((uint32_t)v - vrow * (uint32_t)a.PW);
+        n = (int)fast_div(vrow, dIH);
+        r = (int)(vrow - (uint32_t)n * (uint32_t)a.IH);
+    }
+    for (; j < j_end; ++j, ++v) {
+        if (v == 0) { n = 0; r = 0; vcol = 0; }
+        const bool valid = (v >= 0) && (vcol < a.W) && (r >= a.pad) && (n < a.B);
+        const int h = r - a.pad, w = vcol;
+        const uint32_t dst = base + (uint32_t)j * 16u;
+        const uint32_t nbytes = valid ? 16u : 0u;
+        if constexpr (LOADER == CVAE_LOAD_NHWC) {
+            const __nv_bfloat16* s = valid ? src + (((size_t)n * a.H + h) * a.W + w) * a.src_c + (size_t)q_first * 8 : src;
+            for (int q = sub; q < nplanes; q += g)
+                cp_async16(dst + (uint32_t)q * (uint32_t)plane_stride, valid ? s + q * 8 : src, nbytes);
+        } else {
+            // source [B][2H][2W][C]; plane q <-> (phase ab = q / (C/8), channel chunk q % (C/8))
+            const size_t pix00 = valid ? (((size_t)n * 2 * a.H + 2 * h) * (2 * a.W) + 2 * w) : 0;
+            for (int q = sub; q < nplanes; q += g) {
+                const int qq = q_first + q, ab = qq / cq, cc = qq - ab * cq;
+                const size_t pix = pix00 + (size_t)(ab >> 1) * (2 * a.W) + (ab & 1);
+                cp_async16(dst + (uint32_t)q * (uint32_t)plane_stride, valid ? src + pix * a.src_c + cc * 8 : src, nbytes);
+            }
+        }
+        if (v >= 0 && ++vcol == a.PW) {
+            vcol = 0;
+            if (++r == a.IH) { r = 0; ++n; }
+        }
+    }
+}
 
 template <int LOADER>
 __device__ __forceinline__ void fill_planes(const PlaneSrc& a, uint8_t* planes, int plane_stride,

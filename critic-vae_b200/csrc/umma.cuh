@@ -55,6 +55,19 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* f
     return false;
 }
 
+// One lane of a fully active warp.  tcgen05.mma / commit / bulk copies run on the uniform datapath: issued
+// from `if (lane == 0)` code the compiler wraps each of them in an ELECT + BRA.U.ANY serialisation loop
+// (hundreds of cycles per MMA); under elect.sync it emits them directly.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // Generic-proxy writes (st.shared) must be fenced before the async proxy (UMMA, bulk copy) reads.
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -104,6 +117,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Warp-convergent variants: every lane executes the call, one elected lane issues.  Keeping the C++
+// control flow convergent lets the compiler hold descriptors and loop counters in uniform registers
+// (no R2UR / vector-register chains in front of every UTCHMMA).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+
 // One thread: arrive on `bar` once every previously issued tcgen05.mma has retired.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::

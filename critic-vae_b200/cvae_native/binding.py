@@ -28,7 +28,7 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
                 ("ksize", ctypes.c_int32), ("src_channels", ctypes.c_int32), ("n_total", ctypes.c_int32),
                 ("loader", ctypes.c_int32), ("epilogue", ctypes.c_int32), ("ktab", ctypes.c_int32),
-                ("tm", ctypes.c_int32),
+                ("tm", ctypes.c_int32), ("n_block", ctypes.c_int32),
                 ("src", c_void_p), ("src2", c_void_p), ("wpack", c_void_p), ("bias", c_void_p),
                 ("act", c_void_p), ("out", c_void_p), ("stats", c_void_p)]
 
@@ -47,6 +47,8 @@ lib.cvae_version.restype = c_int
 lib.cvae_check_device_fault.argtypes = [c_void_p]
 lib.cvae_conv_gemm.argtypes = [ctypes.POINTER(ConvDesc), c_void_p]
 lib.cvae_conv_ksteps.argtypes = [c_int, c_int, c_int]
+lib.cvae_conv_debug_counters.argtypes = [c_void_p]
+lib.cvae_conv_debug_counters.restype = None
 lib.cvae_conv_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(WgradDesc)]
 lib.cvae_conv_wgrad_workspace_bytes.restype = c_i64
 lib.cvae_conv_wgrad.argtypes = [ctypes.POINTER(WgradDesc), c_void_p]
@@ -88,7 +90,7 @@ for _name, (_args, _res) in _SIGS.items():
     getattr(lib, _name).restype = _res
 
 EXPORTS = ["cvae_last_error", "cvae_version", "cvae_check_device_fault", "cvae_conv_gemm", "cvae_conv_ksteps",
-           "cvae_conv_wgrad_workspace_bytes", "cvae_conv_wgrad"] + list(_SIGS)
+           "cvae_conv_wgrad_workspace_bytes", "cvae_conv_wgrad", "cvae_conv_debug_counters"] + list(_SIGS)
 
 
 def check(rc: int) -> None:

@@ -63,6 +63,7 @@ typedef struct {
     int32_t n_total;       /* GEMM N, multiple of 16 */
     int32_t loader, epilogue, ktab;
     int32_t tm;            /* 128-pixel tiles per CTA pass; 0 = automatic */
+    int32_t n_block;       /* GEMM columns per work item (16/32/64/128, divides min(n_total,128)); 0 = automatic */
     const void* src;
     const void* src2;
     const void* wpack;     /* packed by cvae_pack_weights */
@@ -73,6 +74,8 @@ typedef struct {
 } cvae_conv_desc;
 
 int cvae_conv_gemm(const cvae_conv_desc* d, void* stream);
+/* profiling aid: device buffer of >= 8 * 148 uint64 cycle counters written by the pipelined kernel (NULL = off) */
+void cvae_conv_debug_counters(void* device_buf);
 /* number of K=16 steps of a conv GEMM: the packed weight tensor is [n_total/nb][ksteps][nb][16] bf16,
  * nb = min(n_total, 128) */
 int cvae_conv_ksteps(int ksize, int src_channels, int ktab);
