@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
         tc_fence_after();
 
         if (warp == 4) {
-            if (lane == 0) {
+            if (elect_one()) {
                 for (int st = 0; st < stages_per_chunk && alive; ++st) {
                     alive = mbar_wait(&bar_empty[ring_stage], ring_phase ^ 1, a.fault);
                     mbar_expect_tx(&bar_full[ring_stage], stage_bytes);
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
             }
             __syncwarp();
         } else if (warp == 5) {
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t planes_addr = smem_u32(planes);
                 const uint32_t wring_addr = smem_u32(wring);
                 for (int st = 0; st < stages_per_chunk && alive; ++st) {

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradAr
         }
     } else {
         // ------------------------------ MMA issuer ---------------------------------------------
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync, not `lane == 0`: the compiler then emits UTCHMMA without an ELECT/BRA.U.ANY loop
             bool alive = true;
             const uint32_t smem_base = smem_u32(smem);
             const uint32_t sbo_a = a.shift_a ? 16u : (uint32_t)a.stride_a;
@@ -183,100 +183,96 @@ __device__ __forceinline__ int phase_tap(int a, int k) {
     return d <= -2 ? 0 : (d <= 0 ? 1 : 2);
 }
 
-__global__ void wgrad_fold_kernel(const FoldArgs f) {
-    const int total_w = f.cout * f.cin * 25;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < total_w) {
-        const int kx = idx % 5, ky = (idx / 5) % 5, ci = (idx / 25) % f.cin, co = idx / (25 * f.cin);
+// One split's contribution to dw[co][ci][ky][kx] (p = that split's partial).
+__device__ __forceinline__ float fold_term(const FoldArgs& f, const float* __restrict__ p, int co, int ci, int ky, int kx) {
+    if (f.kind == CVAE_WGRAD_5X5) {           // group = tap, row = co, col = ci
+        return __ldg(p + ((size_t)(ky * 5 + kx) * f.m_total + co) * f.n + ci);
+    } else if (f.kind == CVAE_WGRAD_PHASE) {  // group = 3x3 tap, row = (a,b,co), col = ci
         float acc = 0.f;
-        for (int s = 0; s < f.splits; ++s) {
-            const float* p = f.partial + (size_t)s * f.split_floats;
-            if (f.kind == CVAE_WGRAD_5X5) {           // group = tap, row = co, col = ci
-                acc += p[((size_t)(ky * 5 + kx) * f.m_total + co) * f.n + ci];
-            } else if (f.kind == CVAE_WGRAD_PHASE) {  // group = 3x3 tap, row = (a,b,co), col = ci
 #pragma unroll
-                for (int ab = 0; ab < 4; ++ab) {
-                    const int t = phase_tap(ab >> 1, ky) * 3 + phase_tap(ab & 1, kx);
-                    acc += p[((size_t)t * f.m_total + ab * f.cout + co) * f.n + ci];
-                }
-            } else if (f.kind == CVAE_WGRAD_SHIFT_FRAMES) {  // group = ky, row = (kx, ch), col = co
-                acc += p[((size_t)ky * f.m_total + kx * 8 + ci) * f.n + co];
-            } else {  // CVAE_WGRAD_SHIFT_PHASE12: group = (plane p, ty), row = (j, e), col = ci; tx = 1 - j
-#pragma unroll
-                for (int ab = 0; ab < 4; ++ab) {
-                    const int ch = ab * 3 + co, pl = ch >> 3, e = ch & 7;
-                    const int ty = phase_tap(ab >> 1, ky), tx = phase_tap(ab & 1, kx);
-                    const int j = 2 - tx;  // tx index 0..2 <-> offset tx-1 = 1 - j
-                    acc += p[((size_t)(pl * 3 + ty) * f.m_total + j * 8 + e) * f.n + ci];
-                }
-            }
+        for (int ab = 0; ab < 4; ++ab) {
+            const int t = phase_tap(ab >> 1, ky) * 3 + phase_tap(ab & 1, kx);
+            acc += __ldg(p + ((size_t)t * f.m_total + ab * f.cout + co) * f.n + ci);
         }
-        f.dw[idx] = acc;
-    } else if (idx < total_w + f.cout && f.dbias != nullptr) {
-        const int co = idx - total_w;
+        return acc;
+    } else if (f.kind == CVAE_WGRAD_SHIFT_FRAMES) {  // group = ky, row = (kx, ch), col = co
+        return __ldg(p + ((size_t)ky * f.m_total + kx * 8 + ci) * f.n + co);
+    } else {  // CVAE_WGRAD_SHIFT_PHASE12: group = (plane p, ty), row = (j, e), col = ci; tx = 1 - j
         float acc = 0.f;
-        for (int s = 0; s < f.splits; ++s) {
-            const float* p = f.partial + (size_t)s * f.split_floats;
-            if (f.kind == CVAE_WGRAD_5X5) {
-                acc += p[f.bias_off + (size_t)co * 16];
-            } else if (f.kind == CVAE_WGRAD_PHASE) {
-                for (int ab = 0; ab < 4; ++ab) acc += p[f.bias_off + (size_t)(ab * f.cout + co) * 16];
-            } else if (f.kind == CVAE_WGRAD_SHIFT_FRAMES) {
-                // ones live in channel 3 of the frame plane: row (kx = 2, ch 3) of group ky = 2
-                acc += p[((size_t)2 * f.m_total + 2 * 8 + 3) * f.n + co];
-            } else {
-                for (int ab = 0; ab < 4; ++ab) {
-                    const int ch = ab * 3 + co, pl = ch >> 3, e = ch & 7;
-                    // ones pseudo-groups: one per plane, rows (j, e); any j sums the same pixels
-                    acc += p[f.bias_off + ((size_t)pl * f.m_total + 0 * 8 + e) * 16];
-                }
-            }
+#pragma unroll
+        for (int ab = 0; ab < 4; ++ab) {
+            const int ch = ab * 3 + co, pl = ch >> 3, e = ch & 7;
+            const int ty = phase_tap(ab >> 1, ky), tx = phase_tap(ab & 1, kx);
+            const int j = 2 - tx;  // tx index 0..2 <-> offset tx-1 = 1 - j
+            acc += __ldg(p + ((size_t)(pl * 3 + ty) * f.m_total + j * 8 + e) * f.n + ci);
         }
-        f.dbias[co] = acc;
+        return acc;
     }
 }
-
-// Bandwidth-shaped fold for the 5X5 / PHASE kinds: one thread per (tap, co, ci) with ci fastest, so the
-// reads of every split are coalesced row segments and the split loop carries four independent loads;
-// the OIHW write is a 100-byte-strided scatter of 4-byte values (10 MB per step in total).
-__global__ void __launch_bounds__(256) wgrad_fold_rows_kernel(const FoldArgs f) {
-    const int total = 25 * f.cout * f.cin;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < total) {
-        const int ci = idx % f.cin, co = (idx / f.cin) % f.cout, tap = idx / (f.cin * f.cout);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        const size_t ss = (size_t)f.split_floats;
-        auto accumulate = [&](size_t off) {
-            const float* p = f.partial + off;
-            int s = 0;
-            for (; s + 4 <= f.splits; s += 4) {
-                a0 += __ldg(p + (size_t)s * ss);
-                a1 += __ldg(p + (size_t)(s + 1) * ss);
-                a2 += __ldg(p + (size_t)(s + 2) * ss);
-                a3 += __ldg(p + (size_t)(s + 3) * ss);
-            }
-            for (; s < f.splits; ++s) a0 += __ldg(p + (size_t)s * ss);
-        };
-        if (f.kind == CVAE_WGRAD_5X5) {
-            accumulate(((size_t)tap * f.m_total + co) * f.n + ci);
-        } else {
-            const int ky = tap / 5, kx = tap - ky * 5;
-#pragma unroll
-            for (int ab = 0; ab < 4; ++ab) {
-                const int t = phase_tap(ab >> 1, ky) * 3 + phase_tap(ab & 1, kx);
-                accumulate(((size_t)t * f.m_total + ab * f.cout + co) * f.n + ci);
-            }
-        }
-        f.dw[((size_t)co * f.cin + ci) * 25 + tap] = (a0 + a1) + (a2 + a3);
-    } else if (idx < total + f.cout && f.dbias != nullptr) {
-        const int co = idx - total;
+__device__ __forceinline__ float fold_bias_term(const FoldArgs& f, const float* __restrict__ p, int co) {
+    if (f.kind == CVAE_WGRAD_5X5) return __ldg(p + f.bias_off + (size_t)co * 16);
+    if (f.kind == CVAE_WGRAD_PHASE) {
         float acc = 0.f;
-        for (int s = 0; s < f.splits; ++s) {
-            const float* p = f.partial + (size_t)s * f.split_floats + f.bias_off;
-            if (f.kind == CVAE_WGRAD_5X5) acc += p[(size_t)co * 16];
-            else for (int ab = 0; ab < 4; ++ab) acc += p[(size_t)(ab * f.cout + co) * 16];
+        for (int ab = 0; ab < 4; ++ab) acc += __ldg(p + f.bias_off + (size_t)(ab * f.cout + co) * 16);
+        return acc;
+    }
+    // frames kind: ones live in channel 3 of the frame plane: row (kx = 2, ch 3) of group ky = 2
+    if (f.kind == CVAE_WGRAD_SHIFT_FRAMES) return __ldg(p + ((size_t)2 * f.m_total + 2 * 8 + 3) * f.n + co);
+    float acc = 0.f;
+    for (int ab = 0; ab < 4; ++ab) {
+        const int ch = ab * 3 + co, pl = ch >> 3, e = ch & 7;
+        // ones pseudo-groups: one per plane, rows (j, e); any j sums the same pixels
+        acc += __ldg(p + f.bias_off + ((size_t)pl * f.m_total + 0 * 8 + e) * 16);
+    }
+    return acc;
+}
+
+// Fold: block = 32 consecutive outputs x 8 split lanes.  Outputs are enumerated with the partial's
+// fastest index innermost, so every warp reads one contiguous 128-byte row segment per split; the
+// split loop is spread over the 8 warps and carries two independent accumulators, then the 8 lane
+// sums are added in a fixed order (bit-reproducible).  The OIHW write is a strided 4-byte scatter
+// (10 MB per step in total).
+static constexpr int kFoldLanes = 8;
+__global__ void __launch_bounds__(256) wgrad_fold_kernel(const FoldArgs f) {
+    __shared__ float red[kFoldLanes][33];
+    const int total_w = 25 * f.cout * f.cin;
+    const int total = total_w + (f.dbias ? f.cout : 0);
+    const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 32 + o;
+    int co = 0, ci = 0, ky = 0, kx = 0;
+    const bool is_w = idx < total_w, is_b = !is_w && idx < total;
+    if (is_w) {
+        int r = idx;
+        if (f.kind == CVAE_WGRAD_5X5 || f.kind == CVAE_WGRAD_PHASE) {            // (tap, co, ci)
+            ci = r % f.cin; r /= f.cin; co = r % f.cout; r /= f.cout; ky = r / 5; kx = r - ky * 5;
+        } else if (f.kind == CVAE_WGRAD_SHIFT_FRAMES) {                          // (ky, kx, ci, co)
+            co = r % f.cout; r /= f.cout; ci = r % f.cin; r /= f.cin; kx = r % 5; ky = r / 5;
+        } else {                                                                 // (co, ky, kx, ci)
+            ci = r % f.cin; r /= f.cin; kx = r % 5; r /= 5; ky = r % 5; co = r / 5;
         }
-        f.dbias[co] = acc;
+    } else if (is_b) {
+        co = idx - total_w;
+    }
+    float a0 = 0.f, a1 = 0.f;
+    const size_t ss = (size_t)f.split_floats;
+    if (is_w) {
+        int s = sl;
+        for (; s + kFoldLanes < f.splits; s += 2 * kFoldLanes) {
+            a0 += fold_term(f, f.partial + (size_t)s * ss, co, ci, ky, kx);
+            a1 += fold_term(f, f.partial + (size_t)(s + kFoldLanes) * ss, co, ci, ky, kx);
+        }
+        if (s < f.splits) a0 += fold_term(f, f.partial + (size_t)s * ss, co, ci, ky, kx);
+    } else if (is_b) {
+        for (int s = sl; s < f.splits; s += kFoldLanes) a0 += fold_bias_term(f, f.partial + (size_t)s * ss, co);
+    }
+    red[sl][o] = a0 + a1;
+    __syncthreads();
+    if (sl == 0 && (is_w || is_b)) {
+        float acc = 0.f;
+#pragma unroll
+        for (int l = 0; l < kFoldLanes; ++l) acc += red[l][o];
+        if (is_w) f.dw[((size_t)co * f.cin + ci) * 25 + ky * 5 + kx] = acc;
+        else f.dbias[co] = acc;
     }
 }
 
@@ -462,12 +458,9 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
 
     f.kind = d->kind; f.cout = d->cout; f.cin = d->cin; f.splits = splits; f.split_floats = a.split_floats;
     f.m_total = a.m_total; f.n = n; f.partial = a.partial; f.dw = (float*)d->dw; f.dbias = (float*)d->dbias;
-    if (d->kind == CVAE_WGRAD_5X5 || d->kind == CVAE_WGRAD_PHASE) {
+    {
         const int total = d->cout * d->cin * 25 + d->cout;
-        wgrad_fold_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(f);
-    } else {
-        const int total = d->cout * d->cin * 25 + d->cout;
-        wgrad_fold_kernel<<<(total + 255) / 256, 256, 0, stream>>>(f);
+        wgrad_fold_kernel<<<(total + 31) / 32, 256, 0, stream>>>(f);
     }
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;

@@ -25,7 +25,7 @@ __host__ __device__ constexpr int lvl_off(int l) {
 }
 static constexpr int kPyr = lvl_off(5);          // 5580 floats
 static constexpr int kMap = 64 * 65;             // one padded 64x64 map
-static constexpr int kMsThreads = 256;
+static constexpr int kMsThreads = 512;
 
 // horizontal 11-tap pass producing NM maps from per-pixel inputs built by `make`.
 // task t -> (row = t % S, segment of 8 columns = t / S)
@@ -128,7 +128,7 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
     float* Hm = Bp + kPyr;            // 5 horizontally blurred maps (reused for the 3 gradient maps)
     float* Dm = Hm + 5 * kMap;        // BWD: 3 derivative maps
     float* G = Dm + (BWD ? 3 * kMap : 0);  // BWD: per-level gradient pyramid
-    __shared__ float scratch[8];
+    __shared__ float scratch[kMsThreads / 32];
     const float C1 = 0.0001f, C2 = 0.0009f;
 
     for (int plane = blockIdx.x; plane < planes; plane += gridDim.x) {
