@@ -762,7 +762,7 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
         const double mma_cyc = (N / 2.0 > 32.0 + N / 4.0 ? N / 2.0 : 32.0 + N / 4.0) * 1.3;
         for (int t : {1, 2, 3, 4, 6, 8}) {
             if (2 * t * N > 512 || (t > 1 && t > total_tiles)) continue;
-            const size_t L = (size_t)t * 128 + 2 * a.halo + 8;
+            const size_t L = ((size_t)t * 128 + 2 * a.halo + 8) | 1;
             const size_t buf = ((size_t)a.planes * L * 16 + 1023) & ~(size_t)1023;
             if (2 * buf + 32 * 1024 > kDynSmemMax) continue;
             const long chunks = (total_tiles + t - 1) / t;
@@ -786,7 +786,7 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     CVAE_REQUIRE(tm >= 1 && 2 * tm * N <= 512, CVAE_EINVAL, "conv_gemm: tm %d x n_block %d exceeds tensor memory", tm, N);
     a.n_blocks = d->n_total / N;
     a.tm = tm;
-    a.L = tm * 128 + 2 * a.halo + 8;
+    a.L = (tm * 128 + 2 * a.halo + 8) | 1;   // odd: the lanes copying the planes of one pixel spread over the banks
     a.plane_stride = a.L * 16;
     a.buf_bytes = (int)((((size_t)a.planes * a.plane_stride) + 1023) & ~(size_t)1023);
     a.num_chunks = (total_tiles + tm - 1) / tm;

@@ -20,7 +20,11 @@
 namespace cvae {
 
 static constexpr int kMaxGroups = 28;
-static constexpr int kWgThreads = 160;  // warps 0-3 loaders + epilogue, warp 4 MMA issuer
+// warps 0 .. kWgLoadWarps-1 load planes (the address arithmetic of a 16-byte-granular gather is latency bound with
+// one warp per scheduler, so there are several per scheduler); warps 0-3 also run the epilogue; the last warp issues MMAs
+static constexpr int kWgLoadWarps = 12;
+static constexpr int kWgLoaders = kWgLoadWarps * 32;
+static constexpr int kWgThreads = kWgLoaders + 32;
 
 struct WgGroup {
     int a_off;    // bytes, relative to the A region of the buffer (includes plane / m-block base)
@@ -41,12 +45,27 @@ struct WgradArgs {
     int stride_a, stride_b;                  // plane strides (bytes)
     int a_region, buf_bytes;                 // bytes
     int ones_planes;                         // 2 when a ones tile follows the B planes
+    int a_planes_cta;                        // A planes one CTA loads (its M block only)
+    FastDiv dPW, dIH;
     int v_begin;
     int split_floats;                        // floats per split in `partial`
     WgGroup g[kMaxGroups];
     float* partial;
     int* fault;
+    unsigned long long* dbg;   // optional per-CTA cycle counters [ctas][8] (cvae_wgrad_debug_counters)
 };
+
+// kWgKS consecutive K steps of one accumulator group, fully unrolled: every descriptor is a base plus an
+// immediate, so the MMAs issue back to back from the uniform datapath (tools/umma_rate.cu: a descriptor
+// rebuilt from vector registers costs >100 cycles per MMA, three times the N = 32 MMA itself).
+static constexpr int kWgKS = 4;
+__device__ __forceinline__ void wg_issue(uint32_t tcol, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate_first) {
+#pragma unroll
+    for (int j = 0; j < kWgKS; ++j)
+        umma_bf16(tcol, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(j * 16)),
+                  ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(j * 16)), idesc, j == 0 ? accumulate_first : 1u);
+}
 
 template <int LA, int LB>
 __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradArgs a) {
@@ -88,33 +107,54 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradAr
 
     const int my_chunks = (a.num_chunks - split + a.splits - 1) / a.splits;  // chunks split, split+S, ...
 
-    if (warp < 4) {
+    if (warp < kWgLoadWarps) {
         // ------------------------------ loaders ------------------------------------------------
+        // bf16 sources go global -> shared with cp.async (zero-fill for the padding), all copies of a chunk in
+        // flight at once; fp32 sources (frames, d_recon) are converted by the threads themselves.  The fill of
+        // chunk i overlaps the MMAs of chunk i-1 (two buffers).
+        constexpr bool kAsyncA = (LA == CVAE_LOAD_NHWC || LA == CVAE_LOAD_S2D);
         bool alive = true;
+        long long t_we = 0, t_issue = 0, t_land = 0, tq = 0;
+        const bool prof = a.dbg != nullptr;
         for (int i = 0; i < my_chunks; ++i) {
             const int buf = i & 1;
             const int c0 = a.v_begin + (split + i * a.splits) * a.kc;
+            if (prof) tq = clock64();
             if (alive) alive = mbar_wait(&bar_empty[buf], ((i >> 1) & 1) ^ 1, a.fault);
+            if (prof) { const long long t = clock64(); t_we += t - tq; tq = t; }
             uint8_t* A = smem + (size_t)buf * a.buf_bytes;
             uint8_t* Bp = A + a.a_region;
-            fill_planes<LA>(a.pa, A, a.stride_a, c0 + a.a_first, a.a_count, tid, 128);
-            fill_planes<LB>(a.pb, Bp, a.stride_b, c0 + a.b_first, a.b_count, tid, 128);
+            if constexpr (kAsyncA)
+                fill_planes_async<LA>(a.pa, a.dPW, a.dIH, A, a.stride_a, c0 + a.a_first, a.a_count, mb * 16, a.a_planes_cta, tid, kWgLoaders);
+            fill_planes_async<LB>(a.pb, a.dPW, a.dIH, Bp, a.stride_b, c0 + a.b_first, a.b_count, 0, a.pb.planes, tid, kWgLoaders);
+            if constexpr (!kAsyncA) fill_planes<LA>(a.pa, A, a.stride_a, c0 + a.a_first, a.a_count, tid, kWgLoaders);
+            if (prof) { const long long t = clock64(); t_issue += t - tq; tq = t; }
+            cp_async_wait_all();
             fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kWgLoaders) : "memory");
             if (tid == 0) mbar_arrive(&bar_full[buf]);
+            if (prof) t_land += clock64() - tq;
         }
+        if (prof && tid == 0) {
+            unsigned long long* o = a.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+            o[3] = t_we; o[4] = t_issue; o[5] = t_land; o[6] = my_chunks;
+        }
+        long long t_ep = prof ? clock64() : 0;
         // ------------------------------ epilogue -----------------------------------------------
         mbar_wait(&bar_acc, 0, a.fault);
         tc_fence_after();
-        const int row = warp * 32 + lane;
+        // warp w reads TMEM lanes 32 (w % 4) .. +31 (hardware rule); the accumulator groups are dealt round-robin
+        // to the kWgLoadWarps / 4 warps that share a lane quarter
+        const int row = (warp & 3) * 32 + lane;
         float* base = a.partial + (size_t)split * a.split_floats;
         uint32_t col = 0;
         for (int g = g0; g < g1; ++g) {
             const int n = a.g[g].n;
+            if ((g - g0) % (kWgLoadWarps / 4) != (warp >> 2)) { col += n; continue; }
             float* o = base + a.g[g].out_off + ((size_t)mb * a.m_rows + row) * n;
             for (int c = 0; c < n; c += 16) {
                 uint32_t raw[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + col + c, raw);
+                tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + col + c, raw);
                 tmem_wait_ld();
                 if (row < a.m_rows) {
                     float4* o4 = reinterpret_cast<float4*>(o + c);
@@ -126,33 +166,52 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradAr
             }
             col += n;
         }
+        if (prof && tid == 0) {
+            unsigned long long* o = a.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+            o[7] = (unsigned long long)(clock64() - t_ep);   // wait for the last MMAs + TMEM -> global
+        }
     } else {
         // ------------------------------ MMA issuer ---------------------------------------------
         if (elect_one()) {   // elect.sync, not `lane == 0`: the compiler then emits UTCHMMA without an ELECT/BRA.U.ANY loop
             bool alive = true;
             const uint32_t smem_base = smem_u32(smem);
-            const uint32_t sbo_a = a.shift_a ? 16u : (uint32_t)a.stride_a;
-            const uint32_t a_mb = a.shift_a ? 0u : (uint32_t)mb * 16u * a.stride_a;
+            // descriptors: low word = (address >> 4) | LBO (128 B) << 16, high word = SBO | version; the K loop
+            // advances both start addresses by 256 B = 16 descriptor units, issued in unrolled groups of kWgKS
+            const uint32_t lbo = (128u >> 4) << 16;
+            const uint32_t a_hi = (((a.shift_a ? 16u : (uint32_t)a.stride_a) >> 4) & 0x3FFFu) | (1u << 14);
+            const uint32_t b_hi = (((uint32_t)a.stride_b >> 4) & 0x3FFFu) | (1u << 14);
+            const int kgroups = a.kc / (16 * kWgKS);
+            const bool prof = a.dbg != nullptr;
+            long long t_wf = 0, tq = 0;
+            const long long t0 = prof ? clock64() : 0;
             for (int i = 0; i < my_chunks && alive; ++i) {
                 const int buf = i & 1;
+                if (prof) tq = clock64();
                 alive = mbar_wait(&bar_full[buf], (i >> 1) & 1, a.fault);
+                if (prof) t_wf += clock64() - tq;
                 tc_fence_after();
-                const uint32_t A = smem_base + (uint32_t)buf * a.buf_bytes;
-                const uint32_t Bp = A + a.a_region;
-                uint32_t col = 0;
+                const uint32_t A16 = ((smem_base + (uint32_t)buf * a.buf_bytes) & 0x3FFFFu) >> 4;
+                const uint32_t B16 = A16 + ((uint32_t)a.a_region >> 4);
+                uint32_t col = tmem_base;
                 for (int g = g0; g < g1; ++g) {
                     const uint32_t idesc = umma_idesc_bf16(a.g[g].n, kMajorMN, kMajorMN);
-                    const uint32_t as = A + a_mb + a.g[g].a_off, bs = Bp + a.g[g].b_off;
-                    for (int k = 0; k < a.kc / 16; ++k) {
-                        const uint64_t da = smem_desc(as + k * 256u, 128u, sbo_a);
-                        const uint64_t db = smem_desc(bs + k * 256u, 128u, (uint32_t)a.stride_b);
-                        umma_bf16(tmem_base + col, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    uint32_t a_lo = (A16 + ((uint32_t)a.g[g].a_off >> 4)) | lbo;
+                    uint32_t b_lo = (B16 + ((uint32_t)a.g[g].b_off >> 4)) | lbo;
+                    wg_issue(col, a_lo, b_lo, a_hi, b_hi, idesc, i > 0 ? 1u : 0u);
+                    for (int kg = 1; kg < kgroups; ++kg) {
+                        a_lo += 16u * kWgKS;
+                        b_lo += 16u * kWgKS;
+                        wg_issue(col, a_lo, b_lo, a_hi, b_hi, idesc, 1u);
                     }
-                    col += a.g[g].n;
+                    col += (uint32_t)a.g[g].n;
                 }
                 umma_commit(&bar_empty[buf]);
             }
             umma_commit(&bar_acc);
+            if (prof) {
+                unsigned long long* o = a.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+                o[0] = (unsigned long long)(clock64() - t0); o[1] = t_wf;
+            }
         }
         __syncwarp();
     }
@@ -171,6 +230,7 @@ struct FoldArgs {
     int m_total;       // rows per group in the partial
     int n;             // columns per normal group
     int bias_off;      // float offset of the ones pseudo-group ([m_total][16]) inside a split, -1: none
+    int dbg_linear;
     const float* partial;
     float* dw;         // [cout][cin][5][5]
     float* dbias;      // [cout]
@@ -227,18 +287,19 @@ __device__ __forceinline__ float fold_bias_term(const FoldArgs& f, const float* 
     return acc;
 }
 
-// Fold: block = 32 consecutive outputs x 8 split lanes.  Outputs are enumerated with the partial's
+// Fold: block = 256 / L consecutive outputs x L split lanes (L = 8 for many splits, fewer for few).  Outputs are enumerated with the partial's
 // fastest index innermost, so every warp reads one contiguous 128-byte row segment per split; the
 // split loop is spread over the 8 warps and carries two independent accumulators, then the 8 lane
 // sums are added in a fixed order (bit-reproducible).  The OIHW write is a strided 4-byte scatter
 // (10 MB per step in total).
-static constexpr int kFoldLanes = 8;
+template <int kFoldLanes>
 __global__ void __launch_bounds__(256) wgrad_fold_kernel(const FoldArgs f) {
-    __shared__ float red[kFoldLanes][33];
+    constexpr int kOut = 256 / kFoldLanes;   // outputs per block
+    __shared__ float red[kFoldLanes][kOut + 1];
     const int total_w = 25 * f.cout * f.cin;
     const int total = total_w + (f.dbias ? f.cout : 0);
-    const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const int idx = blockIdx.x * 32 + o;
+    const int o = threadIdx.x % kOut, sl = threadIdx.x / kOut;
+    const int idx = blockIdx.x * kOut + o;
     int co = 0, ci = 0, ky = 0, kx = 0;
     const bool is_w = idx < total_w, is_b = !is_w && idx < total;
     if (is_w) {
@@ -271,8 +332,81 @@ __global__ void __launch_bounds__(256) wgrad_fold_kernel(const FoldArgs f) {
         float acc = 0.f;
 #pragma unroll
         for (int l = 0; l < kFoldLanes; ++l) acc += red[l][o];
-        if (is_w) f.dw[((size_t)co * f.cin + ci) * 25 + ky * 5 + kx] = acc;
+        if (is_w) f.dw[f.dbg_linear ? (size_t)idx : ((size_t)co * f.cin + ci) * 25 + ky * 5 + kx] = acc;
         else f.dbias[co] = acc;
+    }
+}
+
+// Vectorised fold for the 5X5 / PHASE kinds (ci fastest in the partial, cin % 4 == 0): a thread owns 4
+// consecutive ci of one (tap, co) and reads float4s, so a warp covers a 512-byte row segment per split.
+// Blocks past the weight range compute the bias gradient (scalar path).
+template <int kFoldLanes>
+__global__ void __launch_bounds__(256) wgrad_fold_rows_kernel(const FoldArgs f, int weight_blocks) {
+    constexpr int kOut = 256 / kFoldLanes;   // float4 outputs per block
+    __shared__ float4 red[kFoldLanes][kOut];
+    const int o = threadIdx.x % kOut, sl = threadIdx.x / kOut;
+    const size_t ss = (size_t)f.split_floats;
+    if ((int)blockIdx.x >= weight_blocks) {   // bias: 256 / L outputs per block, scalar
+        const int co = ((int)blockIdx.x - weight_blocks) * kOut + o;
+        float acc = 0.f;
+        if (co < f.cout)
+            for (int s = sl; s < f.splits; s += kFoldLanes) acc += fold_bias_term(f, f.partial + (size_t)s * ss, co);
+        red[sl][o].x = acc;
+        __syncthreads();
+        if (sl == 0 && co < f.cout) {
+            float t = 0.f;
+#pragma unroll
+            for (int l = 0; l < kFoldLanes; ++l) t += red[l][o].x;
+            f.dbias[co] = t;
+        }
+        return;
+    }
+    const int cin4 = f.cin >> 2;
+    const int total4 = 25 * f.cout * cin4;
+    const int idx = blockIdx.x * kOut + o;
+    const bool live = idx < total4;
+    int ci = 0, co = 0, ky = 0, kx = 0;
+    if (live) {
+        int r = idx;
+        ci = (r % cin4) * 4; r /= cin4; co = r % f.cout; r /= f.cout; ky = r / 5; kx = r - ky * 5;
+    }
+    // offsets of the (up to 4) partial rows that fold onto this output
+    size_t off[4];
+    int nsrc = 1;
+    if (f.kind == CVAE_WGRAD_5X5) {
+        off[0] = ((size_t)(ky * 5 + kx) * f.m_total + co) * f.n + ci;
+    } else {
+        nsrc = 4;
+#pragma unroll
+        for (int ab = 0; ab < 4; ++ab) {
+            const int t = phase_tap(ab >> 1, ky) * 3 + phase_tap(ab & 1, kx);
+            off[ab] = ((size_t)t * f.m_total + ab * f.cout + co) * f.n + ci;
+        }
+    }
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    auto add = [](float4& d, const float4 v) { d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w; };
+    if (live) {
+        for (int q = 0; q < nsrc; ++q) {
+            const float* p = f.partial + off[q];
+            int s = sl;
+            for (; s + kFoldLanes < f.splits; s += 2 * kFoldLanes) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (size_t)s * ss));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(s + kFoldLanes) * ss));
+                add(a0, v0);
+                add(a1, v1);
+            }
+            if (s < f.splits) add(a0, __ldg(reinterpret_cast<const float4*>(p + (size_t)s * ss)));
+        }
+    }
+    add(a0, a1);
+    red[sl][o] = a0;
+    __syncthreads();
+    if (sl == 0 && live) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int l = 0; l < kFoldLanes; ++l) add(t, red[l][o]);
+        float* d = f.dw + ((size_t)co * f.cin + ci) * 25 + ky * 5 + kx;
+        d[0] = t.x; d[25] = t.y; d[50] = t.z; d[75] = t.w;
     }
 }
 
@@ -292,6 +426,11 @@ static int launch_wgrad(const WgradArgs& a, size_t smem, dim3 grid, cudaStream_t
 }  // namespace cvae
 
 using namespace cvae;
+
+static unsigned long long* g_wg_dbg = nullptr;
+// Profiling aid: when set, every weight-gradient CTA writes 8 cycle counters to buf[cta * 8 ..]: MMA thread
+// total / wait-for-data; loaders wait-for-buffer / issue / landing wait / chunks; epilogue.
+extern "C" void cvae_wgrad_debug_counters(void* device_buf) { g_wg_dbg = (unsigned long long*)device_buf; }
 
 extern "C" int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d) {
     if (!d) return -1;
@@ -339,7 +478,7 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
         la = (d->kind == CVAE_WGRAD_5X5) ? CVAE_LOAD_NHWC : CVAE_LOAD_S2D;
         a.pa = PlaneSrc{d->batch, H, W, pad, PW, IH, a_planes, (d->kind == CVAE_WGRAD_5X5) ? mtot : d->cout, 0, d->dy, nullptr};
         a.pb = PlaneSrc{d->batch, H, W, pad, PW, IH, b_planes, d->cin, 0, d->x, nullptr};
-        a.ones_planes = 2;
+        a.ones_planes = d->dbias ? 2 : 0;   // no bias gradient wanted (conv in front of BatchNorm): skip the ones group
         a.a_first = 0; a.b_first = -halo;
     } else if (d->kind == CVAE_WGRAD_SHIFT_FRAMES) {
         // A = frames (3 + ones channel, one plane, 16 shifts), B = dY (cout channels)
@@ -367,11 +506,43 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
     }
     a.m_total = a.m_blocks * a.m_rows;
 
-    // chunk size: biggest of 512/256/128 pixels whose double buffer fits
-    const size_t cap = 200 * 1024;
-    int kc = 512;
-    for (;; kc /= 2) {
-        CVAE_REQUIRE(kc >= 64, CVAE_EINVAL, "conv_wgrad: shape does not fit shared memory");
+    a.a_planes_cta = a.shift_a ? a_planes : (a_planes < 16 ? a_planes : 16);
+    a.dPW = make_fastdiv(PW);
+    a.dIH = make_fastdiv(IH);
+
+    // groups per CTA: fill the 512 TMEM columns (every group is n columns wide; the bias pseudo-groups 16)
+    const int bias_groups = (d->kind == CVAE_WGRAD_SHIFT_FRAMES) ? 0 : (d->kind == CVAE_WGRAD_SHIFT_PHASE12 ? 2 : (d->dbias ? 1 : 0));
+    ngroups = (d->kind == CVAE_WGRAD_5X5) ? 25 : (d->kind == CVAE_WGRAD_PHASE ? 9 : (d->kind == CVAE_WGRAD_SHIFT_FRAMES ? 5 : 6));
+    a.groups_total = ngroups + bias_groups;
+    a.gpc = 512 / n;
+    if (a.gpc < 1) a.gpc = 1;
+    while (a.gpc > 1) {   // keep the column total of every set <= 512 including trailing 16-column pseudo-groups
+        bool ok = true;
+        for (int g0 = 0; g0 < a.groups_total && ok; g0 += a.gpc) {
+            int cols = 0;
+            for (int g = g0; g < g0 + a.gpc && g < a.groups_total; ++g) cols += (g < ngroups) ? n : 16;
+            ok = cols <= 512;
+        }
+        if (ok) break;
+        --a.gpc;
+    }
+    const int gsets = (a.groups_total + a.gpc - 1) / a.gpc;
+    a.gpc = (a.groups_total + gsets - 1) / gsets;   // same number of sets, balanced
+    int splits = d->splits > 0 ? d->splits : (sm_count() / (gsets * a.m_blocks));
+    if (splits < 1) splits = 1;
+
+    // chunk size: the largest multiple of 16 pixels whose double buffer fits, but small enough that every
+    // CTA still gets ~4 chunks to pipeline
+    const size_t cap = 216 * 1024;
+    long per_cta = (total_v + splits - 1) / splits;
+    const int kq = 16 * kWgKS;   // the MMA issuer unrolls kWgKS K steps
+    int kc_want = (int)(((per_cta + 3) / 4 + kq - 1) / kq * kq);
+    if (kc_want < 64) kc_want = 64;
+    if (kc_want > 512) kc_want = 512;
+    if (getenv("CVAE_WG_KC")) kc_want = atoi(getenv("CVAE_WG_KC")) / kq * kq;
+    int kc = kc_want;
+    for (;; kc -= kq) {
+        CVAE_REQUIRE(kc >= kq, CVAE_EINVAL, "conv_wgrad: shape does not fit shared memory");
         a.kc = kc;
         if (a.shift_a) {
             a.a_count = kc + 16 + (d->kind == CVAE_WGRAD_SHIFT_FRAMES ? 4 * PW : 0);
@@ -380,14 +551,20 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
             a.a_count = kc;
             a.b_count = kc + 2 * halo;
         }
-        a.stride_a = a.a_count * 16;
-        a.stride_b = a.b_count * 16;
-        const int a_planes_alloc = a.shift_a ? a_planes : (a_planes < 16 ? 16 : a_planes);
+        // odd plane strides (in 16-byte slots): the 8 lanes that copy the 8 planes of one pixel hit 8 different
+        // bank groups instead of one
+        a.stride_a = (a.a_count | 1) * 16;
+        a.stride_b = (a.b_count | 1) * 16;
+        // an M = 128 MMA reads 16 plane-strided core-matrix groups: keep them inside the buffer even when
+        // fewer planes are real (their accumulator rows are never stored)
+        const int a_planes_alloc = a.shift_a ? a_planes : 16;
         a.a_region = (a_planes_alloc * a.stride_a + 1023) & ~1023;
         a.buf_bytes = (a.a_region + (b_planes + a.ones_planes) * a.stride_b + 1023) & ~1023;
         if ((size_t)2 * a.buf_bytes <= cap && a.buf_bytes < (1 << 17)) break;
     }
     a.num_chunks = (int)((total_v + kc - 1) / kc);
+    if (splits > a.num_chunks) splits = a.num_chunks;
+    a.splits = splits;
 
     // groups
     int gi = 0, out_off = 0;
@@ -398,9 +575,12 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
             a.g[gi++] = WgGroup{0, (halo + dy * PW + dx) * 16, n, out_off};
             out_off += a.m_total * n;
         }
-        f.bias_off = out_off;
-        a.g[gi++] = WgGroup{0, b_planes * a.stride_b + halo * 16, 16, out_off};
-        out_off += a.m_total * 16;
+        f.bias_off = -1;
+        if (d->dbias) {
+            f.bias_off = out_off;
+            a.g[gi++] = WgGroup{0, b_planes * a.stride_b + halo * 16, 16, out_off};
+            out_off += a.m_total * 16;
+        }
     } else if (d->kind == CVAE_WGRAD_SHIFT_FRAMES) {
         for (int ky = 0; ky < 5; ++ky) {
             a.g[gi++] = WgGroup{((ky - 2) * PW - 2 - a.a_first) * 16, 0, n, out_off};
@@ -419,36 +599,21 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
             out_off += a.m_total * 16;
         }
     }
-    a.groups_total = gi;
+    CVAE_REQUIRE(gi == a.groups_total, CVAE_EINVAL, "conv_wgrad: internal group count");
     a.split_floats = out_off;
-    // groups per CTA: fill the 512 TMEM columns
-    a.gpc = 512 / n;
-    if (a.gpc < 1) a.gpc = 1;
-    {   // keep the column total of every set <= 512 including a trailing 16-column pseudo-group
-        while (a.gpc > 1) {
-            bool ok = true;
-            for (int g0 = 0; g0 < a.groups_total && ok; g0 += a.gpc) {
-                int cols = 0;
-                for (int g = g0; g < g0 + a.gpc && g < a.groups_total; ++g) cols += a.g[g].n;
-                ok = cols <= 512;
-            }
-            if (ok) break;
-            --a.gpc;
-        }
-    }
-    const int gsets = (a.groups_total + a.gpc - 1) / a.gpc;
-    int splits = d->splits > 0 ? d->splits : (sm_count() / (gsets * a.m_blocks));
-    if (splits < 1) splits = 1;
-    if (splits > a.num_chunks) splits = a.num_chunks;
-    a.splits = splits;
     a.partial = (float*)d->workspace;
     a.fault = fault_flag();
+    a.dbg = g_wg_dbg;
     CVAE_REQUIRE(a.fault != nullptr, CVAE_ECUDA, "conv_wgrad: fault flag unavailable");
     CVAE_REQUIRE((int64_t)splits * a.split_floats * 4 <= cvae_conv_wgrad_workspace_bytes(d), CVAE_EINVAL,
                  "conv_wgrad: workspace too small");
 
     const size_t smem = (size_t)2 * a.buf_bytes;
     dim3 grid(splits, gsets, a.m_blocks);
+    if (getenv("CVAE_DEBUG"))
+        fprintf(stderr, "conv_wgrad kind %d B=%d %dx%d cout=%d cin=%d: n=%d groups=%d gpc=%d gsets=%d mblocks=%d splits=%d kc=%d chunks=%d "
+                        "buf=%d B smem=%zu\n", d->kind, d->batch, H, W, d->cout, d->cin, n, a.groups_total, a.gpc, gsets, a.m_blocks, splits,
+                a.kc, a.num_chunks, a.buf_bytes, (size_t)2 * a.buf_bytes);
     int rc;
     if (la == CVAE_LOAD_NHWC) rc = launch_wgrad<CVAE_LOAD_NHWC, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     else if (la == CVAE_LOAD_S2D) rc = launch_wgrad<CVAE_LOAD_S2D, CVAE_LOAD_NHWC>(a, smem, grid, stream);
@@ -456,11 +621,26 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
     else rc = launch_wgrad<CVAE_LOAD_S2D_NCHW3_DTANH, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     if (rc != CVAE_OK) return rc;
 
+    f.dbg_linear = getenv("CVAE_FOLD_LINEAR") ? 1 : 0;
     f.kind = d->kind; f.cout = d->cout; f.cin = d->cin; f.splits = splits; f.split_floats = a.split_floats;
     f.m_total = a.m_total; f.n = n; f.partial = a.partial; f.dw = (float*)d->dw; f.dbias = (float*)d->dbias;
     {
         const int total = d->cout * d->cin * 25 + d->cout;
-        wgrad_fold_kernel<<<(total + 31) / 32, 256, 0, stream>>>(f);
+        if (d->kind == CVAE_WGRAD_5X5 || d->kind == CVAE_WGRAD_PHASE) {
+            const int total4 = d->cout * d->cin * 25 / 4;
+#define CVAE_FOLD_ROWS(L_)                                                                            \
+    {                                                                                                 \
+        const int wb = (total4 + 256 / (L_) - 1) / (256 / (L_));                                      \
+        const int bb = f.dbias ? (d->cout + 256 / (L_) - 1) / (256 / (L_)) : 0;                       \
+        wgrad_fold_rows_kernel<L_><<<wb + bb, 256, 0, stream>>>(f, wb);                               \
+    }
+            if (splits >= 48) CVAE_FOLD_ROWS(8)
+            else if (splits >= 16) CVAE_FOLD_ROWS(4)
+            else CVAE_FOLD_ROWS(2)
+#undef CVAE_FOLD_ROWS
+        } else {
+            wgrad_fold_kernel<8><<<(total + 31) / 32, 256, 0, stream>>>(f);
+        }
     }
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;

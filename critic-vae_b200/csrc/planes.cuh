@@ -45,6 +45,13 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, 
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // Asynchronous plane fill (cp.async, 16 bytes per copy, zero-fill for padding) for the bf16 loaders.
 // Planes [q_first, q_first + nplanes) of the source are written to planes 0.. of the buffer.

@@ -49,6 +49,8 @@ lib.cvae_conv_gemm.argtypes = [ctypes.POINTER(ConvDesc), c_void_p]
 lib.cvae_conv_ksteps.argtypes = [c_int, c_int, c_int]
 lib.cvae_conv_debug_counters.argtypes = [c_void_p]
 lib.cvae_conv_debug_counters.restype = None
+lib.cvae_wgrad_debug_counters.argtypes = [c_void_p]
+lib.cvae_wgrad_debug_counters.restype = None
 lib.cvae_conv_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(WgradDesc)]
 lib.cvae_conv_wgrad_workspace_bytes.restype = c_i64
 lib.cvae_conv_wgrad.argtypes = [ctypes.POINTER(WgradDesc), c_void_p]

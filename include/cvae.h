@@ -103,6 +103,8 @@ typedef struct {
 } cvae_wgrad_desc;
 
 int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d);
+/* profiling aid: device buffer of >= 8 * (CTAs of the launch) uint64 cycle counters (NULL = off) */
+void cvae_wgrad_debug_counters(void* device_buf);
 int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

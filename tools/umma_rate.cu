@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_rate tools/umma_rate.cu && tools/umma_rate
 #include "../critic-vae_b200/csrc/umma.cuh"
 #include <stdio.h>
+#include <string.h>
 #include <stdlib.h>
 
 using namespace cvae;
@@ -351,8 +352,80 @@ static void run(const char* name, RateArgs p, int grid) {
     cudaFree(d);
 }
 
-int main() {
+
+// Tight loop with both start addresses advancing 256 B per MMA (the weight-gradient K loop) and the majors /
+// strides taken from the arguments; B sits at +96 KB.  `sbo` values are plane strides.
+__global__ void __launch_bounds__(128, 1) mn_kernel(RateArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (uint32_t i = tid * 16; i < 200 * 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (warp == 0) {
+        const uint32_t idesc = umma_idesc_bf16(p.n, p.a_major, p.b_major);
+        const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 96 * 1024;
+        if (elect_one()) {
+            const uint64_t da = desc_full(sa, p.a_lbo, p.a_sbo, 0), db = desc_full(sb, p.b_lbo, p.b_sbo, 0);
+            const long long t0 = clock64();
+            for (uint32_t r = 0; r < p.reps; r += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) umma_bf16(tmem_base + (u & 3) * p.n * (p.accs > 1), da + (uint64_t)(u * 16), db + (uint64_t)(u * 16), idesc, 1u);
+            }
+            umma_commit(&bar);
+            mbar_wait(&bar, 0, &g_rate_fault);
+            p.out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem_base, 512);
+}
+static void run_mn(const char* name, RateArgs p, int grid) {
+    unsigned long long* d;
+    cudaMalloc(&d, grid * 8);
+    cudaMemset(d, 0, grid * 8);
+    p.out = d;
+    cudaFuncSetAttribute(mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    mn_kernel<<<grid, 128, 200 * 1024>>>(p);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%-44s ERROR %s\n", name, cudaGetErrorString(e)); exit(1); }
+    unsigned long long h[148];
+    cudaMemcpy(h, d, grid * 8, cudaMemcpyDeviceToHost);
+    double sum = 0;
+    for (int i = 0; i < grid; ++i) sum += (double)h[i];
+    printf("%-48s N=%3u accs=%u grid=%3d : %7.1f cycles/MMA (N/2 = %u)\n", name, p.n, p.accs, grid, sum / grid / p.reps, p.n / 2);
+    cudaFree(d);
+}
+
+int main(int argc, char** argv) {
     const uint32_t reps = 960;
+    if (argc > 1 && !strcmp(argv[1], "mn")) {
+        // weight-gradient layouts: operands MN-major (16 B = 8 M/N elements, pixel slots = K), LBO 128,
+        // SBO = plane stride (plane = 256 pixel slots here); the start address advances 256 B (16 pixels) per MMA
+        for (int grid : {1, 148})
+            for (uint32_t n : {16u, 32u, 64u, 128u, 256u})
+                for (uint32_t accs : {1u, 4u}) {
+                    if (accs * n > 512) continue;
+                    const uint32_t ps = 257 * 16;
+                    RateArgs p{n, accs, reps, 128, ps, 128, ps, 0, 0, 0, 256, 256, kMajorMN, kMajorMN, nullptr};
+                    if (n * ps <= 8 * 100 * 1024) run_mn("MN-major A and B", p, grid);
+                    RateArgs q{n, accs, reps, 128, 16, 128, ps, 0, 0, 0, 256, 256, kMajorMN, kMajorMN, nullptr};
+                    run_mn("MN-major, shift-trick A (SBO 16)", q, grid);
+                    RateArgs r{n, accs, reps, ps, 128, 128, ps, 0, 0, 0, 256, 256, kMajorK, kMajorMN, nullptr};
+                    run_mn("K-major A (SBO 128, LBO plane), MN-major B", r, grid);
+                    RateArgs t{n, accs, reps, ps, 128, 128, 256, 0, 0, 0, 256, 256, kMajorK, kMajorK, nullptr};
+                    run_mn("K-major A, K-major packed B", t, grid);
+                }
+        return 0;
+    }
     for (uint32_t n : {64u, 128u}) {
         run_r2ur<8, 0>(n); run_r2ur<8, 1>(n); run_r2ur<8, 2>(n); run_r2ur<8, 3>(n);
         run_r2ur<4, 0>(n); run_r2ur<4, 1>(n); run_r2ur<4, 3>(n);
