@@ -92,7 +92,7 @@ for _name, (_args, _res) in _SIGS.items():
     getattr(lib, _name).restype = _res
 
 EXPORTS = ["cvae_last_error", "cvae_version", "cvae_check_device_fault", "cvae_conv_gemm", "cvae_conv_ksteps",
-           "cvae_conv_wgrad_workspace_bytes", "cvae_conv_wgrad", "cvae_conv_debug_counters"] + list(_SIGS)
+           "cvae_conv_wgrad_workspace_bytes", "cvae_conv_wgrad", "cvae_conv_debug_counters", "cvae_wgrad_debug_counters"] + list(_SIGS)
 
 
 def check(rc: int) -> None:
