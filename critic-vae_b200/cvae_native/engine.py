@@ -107,6 +107,9 @@ class VAEEngine:
         self._ws = {}
         self._wgrad_ws = None
         self.profile = None
+        # Weight gradients are leaves of the backward pass: with a side stream they run concurrently with the
+        # data-gradient chain (fork / join with events, so the pair is CUDA-graph capturable).
+        self.side_stream = None
 
     # ---- parameters ---------------------------------------------------------------------------
     def view(self, name, buf=None):
@@ -243,7 +246,15 @@ class VAEEngine:
         # the zero-initialised slot of the flat buffer untouched instead of writing rounding noise.
         d.dw, d.workspace = _ptr(self.view(name + ".weight", g)), _ptr(self._wgrad_ws)
         d.dbias = None if name.startswith("encoder.") else _ptr(self.view(name + ".bias", g))
-        self._timed("conv_wgrad", lambda: L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr())))
+        if self.side_stream is None or self.profile is not None:
+            self._timed("conv_wgrad", lambda: L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr())))
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.side_stream.wait_event(ev)
+        with torch.cuda.stream(self.side_stream):
+            L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()))
+        self._side_used = True
 
     def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None):
         """Gradients of every parameter into the flat buffer `g` (default self.gflat), given the
@@ -251,6 +262,7 @@ class VAEEngine:
         g = self.gflat if g is None else g
         B, s = ws.B, L.stream_ptr()
         G = lambda n: self.view(n, g)
+        self._side_used = False
         dm = "decoder.model."
         # D4 .. D1: up-sample-folded convs
         self._wgrad(g, dm + "12", kind=L.WGRAD_SHIFT_PHASE12, batch=B, height=32, width=32, cout=3, cin=32,
@@ -288,6 +300,8 @@ class VAEEngine:
                 self._wgrad(g, cname, kind=L.WGRAD_5X5, batch=B, height=h, width=h, cout=co, cin=ci, x=ws.a[i - 1], dy=ws.g_c[i])
                 self._conv(batch=B, height=h, width=h, ksize=5, src_channels=co, n_total=ci, loader=L.LOAD_NHWC,
                            epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
+        if self._side_used:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
         return g
 
     # ---- optimizer ----------------------------------------------------------------------------

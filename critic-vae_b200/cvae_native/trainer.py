@@ -13,6 +13,8 @@ libcvae.so.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import binding as L
@@ -36,6 +38,8 @@ class TrainStep:
         self.critic_w = critic._weights() if critic is not None else None
         self.losses = self.ws.losses
         self._graphs = None
+        if os.environ.get("CVAE_NO_SIDE_STREAM") is None:
+            self.eng.side_stream = torch.cuda.Stream()
         self._use_graph = use_graph
         self.launches_per_step = None
 
@@ -44,9 +48,22 @@ class TrainStep:
         eng, ws, s = self.eng, self.ws, L.stream_ptr()
         if from_u8:
             L.check(L.lib.cvae_frames_u8_to_f32(self.B, self.x_u8.data_ptr(), self.x.data_ptr(), s))
+        side, joined = eng.side_stream, None
         if self.critic_w is not None:
-            L.check(L.lib.cvae_critic_fwd(self.B, self.x.data_ptr(), self.critic_w.data_ptr(), self.pred.data_ptr(), s))
+            if side is None:
+                L.check(L.lib.cvae_critic_fwd(self.B, self.x.data_ptr(), self.critic_w.data_ptr(), self.pred.data_ptr(), s))
+            else:   # the critic value is only needed by the decoder: score the frames beside the encoder
+                fork = torch.cuda.Event()
+                fork.record()
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    L.check(L.lib.cvae_critic_fwd(self.B, self.x.data_ptr(), self.critic_w.data_ptr(), self.pred.data_ptr(),
+                                                  L.stream_ptr()))
+                    joined = torch.cuda.Event()
+                    joined.record()
         eng.encode(self.x, True, ws)
+        if joined is not None:
+            torch.cuda.current_stream().wait_event(joined)
         eng.decode(self.pred, self.eps, True, ws)
         eng.loss_forward(ws.recon, self.x, ws.ml, ws)
         eng.loss_backward(ws.recon, self.x, ws.ml, ws)
