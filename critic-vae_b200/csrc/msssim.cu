@@ -3,7 +3,8 @@
 //
 // One CTA per (frame, channel) plane keeps both image pyramids in shared memory and runs the 11x11
 // window as two separable 11-tap passes (the reference window is an outer product, vae_nets.py:175-179)
-// with 8 outputs per thread per pass so the FP32 pipe, not shared-memory bandwidth, is the limiter.
+// with up to 8 outputs per thread per pass so the FP32 pipe, not shared-memory bandwidth, is the limiter;
+// all five pyramid levels go through each pass together.
 // The MS-SSIM means are batch-global (vae_nets.py:207,212) and enter the loss non-linearly
 // (vae_nets.py:243-246), hence two phases: forward accumulates the ten level sums with double
 // atomics, loss_finalize turns them into the loss and the per-level chain-rule coefficients, and
@@ -27,94 +28,106 @@ static constexpr int kPyr = lvl_off(5);          // 5580 floats
 static constexpr int kMap = 64 * 65;             // one padded 64x64 map
 static constexpr int kMsThreads = 512;
 
-// horizontal 11-tap pass producing NM maps from per-pixel inputs built by `make`.
-// task t -> (row = t % S, segment of 8 columns = t / S)
-template <int NM, typename Make>
-__device__ __forceinline__ void hpass(int S, const Window& w, float* __restrict__ out, Make make) {
-    const int st = S + 1, nseg = (S + 7) >> 3;
-    for (int t = threadIdx.x; t < S * nseg; t += kMsThreads) {
-        const int r = t % S, c0 = (t / S) * 8;
-        float acc[NM][8];
+// Every "map" below is a pyramid-shaped buffer (kPyr floats): level l of map m sits at m * kPyr + lvl_off(l).
+//
+// Task decomposition.  In every phase a thread runs ONE level-0 task (8 outputs; 64 rows x 8 segments = 512
+// tasks = one per thread) and at most ONE task of the coarser levels, whose tasks are made finer so the whole
+// tail of the pyramid is a single round as well (warp-aligned ranges):
+//   threads   0..255  level 1, 4 outputs (32 x 8 tasks)      threads 384..447  level 3, 1 output (8 x 8)
+//   threads 256..383  level 2, 2 outputs (16 x 8 tasks)      threads 448..463  level 4, 1 output (4 x 4)
+// Running the five levels one after the other (the first version) left the small levels latency bound: a
+// level costs one full dependent 11-tap chain per thread no matter how few threads have work.
+__device__ __forceinline__ void small_task(int tid, int& level, int& out, int& t) {
+    if (tid < 256) { level = 1; out = 4; t = tid; }
+    else if (tid < 384) { level = 2; out = 2; t = tid - 256; }
+    else if (tid < 448) { level = 3; out = 1; t = tid - 384; }
+    else if (tid < 464) { level = 4; out = 1; t = tid - 448; }
+    else { level = -1; out = 0; t = 0; }
+}
+
+// horizontal 11-tap pass of task t (row = t % S, OUT columns from (t / S) * OUT) producing NM maps from
+// per-pixel inputs built by `make`.
+template <int NM, int OUT, typename Make>
+__device__ __forceinline__ void hpass(int S, int t, const Window& w, float* __restrict__ out, Make make) {
+    const int st = S + 1;
+    const int r = t % S, c0 = (t / S) * OUT;
+    float acc[NM][OUT];
 #pragma unroll
-        for (int m = 0; m < NM; ++m)
+    for (int m = 0; m < NM; ++m)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[m][j] = 0.f;
+        for (int j = 0; j < OUT; ++j) acc[m][j] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 18; ++i) {
-            const int c = c0 - 5 + i;
+    for (int i = 0; i < OUT + 10; ++i) {
+        const int c = c0 - 5 + i;
+        float v[NM];
+        if (c >= 0 && c < S) make(r * st + c, v);
+        else {
+#pragma unroll
+            for (int m = 0; m < NM; ++m) v[m] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < OUT; ++j) {
+            const int k = i - j;  // tap index: input c = (c0+j) - 5 + k
+            if (k >= 0 && k < 11) {
+#pragma unroll
+                for (int m = 0; m < NM; ++m) acc[m][j] = fmaf(w.g[k], v[m], acc[m][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < OUT; ++j)
+        if (c0 + j < S) {
+#pragma unroll
+            for (int m = 0; m < NM; ++m) out[m * kPyr + r * st + c0 + j] = acc[m][j];
+        }
+}
+
+// vertical 11-tap pass of task t (column = t % S, OUT rows from (t / S) * OUT) over NM maps;
+// `sink(idx, vals)` consumes the blurred values of pixel idx.
+template <int NM, int OUT, typename Sink>
+__device__ __forceinline__ void vpass(int S, int t, const Window& w, const float* __restrict__ in, Sink sink) {
+    const int st = S + 1;
+    const int c = t % S, r0 = (t / S) * OUT;
+    float acc[NM][OUT];
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int j = 0; j < OUT; ++j) acc[m][j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < OUT + 10; ++i) {
+        const int r = r0 - 5 + i;
+        if (r >= 0 && r < S) {
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const float v = in[m * kPyr + r * st + c];
+#pragma unroll
+                for (int j = 0; j < OUT; ++j) {
+                    const int k = i - j;
+                    if (k >= 0 && k < 11) acc[m][j] = fmaf(w.g[k], v, acc[m][j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < OUT; ++j)
+        if (r0 + j < S) {
             float v[NM];
-            if (c >= 0 && c < S) make(r * st + c, v);
-            else {
 #pragma unroll
-                for (int m = 0; m < NM; ++m) v[m] = 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = i - j;  // tap index: input c = (c0+j) - 5 + k
-                if (k >= 0 && k < 11) {
-#pragma unroll
-                    for (int m = 0; m < NM; ++m) acc[m][j] = fmaf(w.g[k], v[m], acc[m][j]);
-                }
-            }
+            for (int m = 0; m < NM; ++m) v[m] = acc[m][j];
+            sink((r0 + j) * st + c, v);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (c0 + j < S) {
-#pragma unroll
-                for (int m = 0; m < NM; ++m) out[m * kMap + r * st + c0 + j] = acc[m][j];
-            }
-    }
 }
 
-// vertical 11-tap pass over NM maps; `sink(idx, vals)` consumes the blurred values of pixel idx.
-template <int NM, typename Sink>
-__device__ __forceinline__ void vpass(int S, const Window& w, const float* __restrict__ in, Sink sink) {
-    const int st = S + 1, nseg = (S + 7) >> 3;
-    for (int t = threadIdx.x; t < S * nseg; t += kMsThreads) {
-        const int c = t % S, r0 = (t / S) * 8;
-        float acc[NM][8];
-#pragma unroll
-        for (int m = 0; m < NM; ++m)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[m][j] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 18; ++i) {
-            const int r = r0 - 5 + i;
-            if (r >= 0 && r < S) {
-#pragma unroll
-                for (int m = 0; m < NM; ++m) {
-                    const float v = in[m * kMap + r * st + c];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = i - j;
-                        if (k >= 0 && k < 11) acc[m][j] = fmaf(w.g[k], v, acc[m][j]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (r0 + j < S) {
-                float v[NM];
-#pragma unroll
-                for (int m = 0; m < NM; ++m) v[m] = acc[m][j];
-                sink((r0 + j) * st + c, v);
-            }
+// run `body(level, S, OUT-tag, task)` for this thread's level-0 task and its coarse-level task
+#define CVAE_MS_FOR_TASKS(...)                                                   \
+    {                                                                            \
+        { constexpr int OUT = 8; const int lvl = 0, S = 64, t = threadIdx.x; __VA_ARGS__ } \
+        int lvl_, out_, t_;                                                      \
+        small_task(threadIdx.x, lvl_, out_, t_);                                 \
+        if (out_ == 4) { constexpr int OUT = 4; const int lvl = 1, S = 32, t = t_; __VA_ARGS__ }        \
+        else if (out_ == 2) { constexpr int OUT = 2; const int lvl = 2, S = 16, t = t_; __VA_ARGS__ }   \
+        else if (out_ == 1) { constexpr int OUT = 1; const int lvl = lvl_, S = 64 >> lvl_, t = t_; __VA_ARGS__ } \
     }
-}
-
-__device__ __forceinline__ float block_sum(float v, float* scratch) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float s = 0.f;
-    if (threadIdx.x < 32) {
-        s = threadIdx.x < (kMsThreads >> 5) ? scratch[threadIdx.x] : 0.f;
-        s = warp_sum(s);
-    }
-    return s;  // valid in warp 0
-}
 
 // coef layout (floats): [0..3] dL/d(cs_map pixel) for levels 0..3, [4] dL/d(ssim_map pixel) level 4
 template <bool BWD>
@@ -126,10 +139,15 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
     float* A = sm;                    // recon pyramid
     float* Bp = A + kPyr;             // target pyramid
     float* Hm = Bp + kPyr;            // 5 horizontally blurred maps (reused for the 3 gradient maps)
-    float* Dm = Hm + 5 * kMap;        // BWD: 3 derivative maps
-    float* G = Dm + (BWD ? 3 * kMap : 0);  // BWD: per-level gradient pyramid
-    __shared__ float scratch[kMsThreads / 32];
+    float* Dm = Hm + 5 * kPyr;        // BWD: 3 derivative maps; map 0 is reused for the per-level gradient G
+    __shared__ float wsum[2][2][kMsThreads / 32];   // [level-0 | coarse level][cs | ssim][warp]
     const float C1 = 0.0001f, C2 = 0.0009f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gcoef[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (BWD) {
+#pragma unroll
+        for (int l = 0; l < 5; ++l) gcoef[l] = coef[l];
+    }
 
     for (int plane = blockIdx.x; plane < planes; plane += gridDim.x) {
         const float* ra = recon + (size_t)plane * 4096;
@@ -154,18 +172,23 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
             __syncthreads();
         }
 
-        for (int l = 0; l < kLevels; ++l) {
-            const int S = lvl_size(l);
-            const float* a = A + lvl_off(l);
-            const float* b = Bp + lvl_off(l);
-            hpass<5>(S, w, Hm, [&](int idx, float* v) {
+        // ---- phase 1: horizontal blur of (a, b, a*a, b*b, a*b), all levels ----
+        CVAE_MS_FOR_TASKS({
+            const float* a = A + lvl_off(lvl);
+            const float* b = Bp + lvl_off(lvl);
+            hpass<5, OUT>(S, t, w, Hm + lvl_off(lvl), [&](int idx, float* v) {
                 const float av = a[idx], bv = b[idx];
                 v[0] = av; v[1] = bv; v[2] = av * av; v[3] = bv * bv; v[4] = av * bv;
             });
-            __syncthreads();
+        })
+        __syncthreads();
+        // ---- phase 2: vertical blur -> SSIM / CS maps (forward: sums; backward: derivative maps) ----
+        float acc_cs[2] = {0.f, 0.f}, acc_ss[2] = {0.f, 0.f};
+        CVAE_MS_FOR_TASKS({
+            const float gc = BWD ? gcoef[lvl < 4 ? lvl : 4] : 0.f;
+            float* dm = Dm + lvl_off(lvl);
             float cs_acc = 0.f, ss_acc = 0.f;
-            const float gc = BWD ? coef[l < 4 ? l : 4] : 0.f;
-            vpass<5>(S, w, Hm, [&](int idx, const float* v) {
+            vpass<5, OUT>(S, t, w, Hm + lvl_off(lvl), [&](int idx, const float* v) {
                 const float mu1 = v[0], mu2 = v[1];
                 const float s1 = v[2] - mu1 * mu1, s2 = v[3] - mu2 * mu2, s12 = v[4] - mu1 * mu2;
                 const float v1 = 2.f * s12 + C2, v2 = s1 + s2 + C2;
@@ -176,7 +199,7 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
                 if (BWD) {
                     // derivative of the level's scalar w.r.t. mu1, blur(a*a), blur(a*b) at this pixel
                     float dmu, daa, dab;
-                    if (l < 4) {           // cs = v1 / v2
+                    if (lvl < 4) {         // cs = v1 / v2
                         dab = 2.f / v2;
                         daa = -v1 / (v2 * v2);
                         dmu = (-2.f * mu2) / v2 + (v1 / (v2 * v2)) * (2.f * mu1);
@@ -187,35 +210,50 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
                         daa = dv2;
                         dmu = dv1 * (-2.f * mu2) + dv2 * (-2.f * mu1) + da1 * (2.f * mu2) + da2 * (2.f * mu1);
                     }
-                    Dm[idx] = dmu * gc;
-                    Dm[kMap + idx] = daa * gc;
-                    Dm[2 * kMap + idx] = dab * gc;
+                    dm[idx] = dmu * gc;
+                    dm[kPyr + idx] = daa * gc;
+                    dm[2 * kPyr + idx] = dab * gc;
                 }
             });
-            if (!BWD) {
-                const float cs_tot = block_sum(cs_acc, scratch);
-                const float ss_tot = block_sum(ss_acc, scratch);
-                if (threadIdx.x == 0) {
-                    atomicAdd(sums + l, (double)cs_tot);
-                    atomicAdd(sums + 5 + l, (double)ss_tot);
-                }
+            acc_cs[lvl > 0] = cs_acc;
+            acc_ss[lvl > 0] = ss_acc;
+        })
+        if (!BWD) {
+            // per-warp partial sums; a warp's coarse-level tasks all belong to one level (warp-aligned ranges)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float c = warp_sum(acc_cs[q]), s2 = warp_sum(acc_ss[q]);
+                if (lane == 0) { wsum[q][0][warp] = c; wsum[q][1][warp] = s2; }
             }
             __syncthreads();
-            if (BWD) {
-                // dL/da_l(q) = blur(dmu)(q) + 2 a(q) blur(daa)(q) + b(q) blur(dab)(q)   (symmetric window)
-                hpass<3>(S, w, Hm, [&](int idx, float* v) {
-                    v[0] = Dm[idx]; v[1] = Dm[kMap + idx]; v[2] = Dm[2 * kMap + idx];
+            if (threadIdx.x < 10) {
+                const int which = threadIdx.x / 5, l = threadIdx.x % 5;
+                // warps of level l in the coarse ranges: L1 0-7, L2 8-11, L3 12-13, L4 14
+                const int w0 = l == 0 ? 0 : (l == 1 ? 0 : (l == 2 ? 8 : (l == 3 ? 12 : 14)));
+                const int w1 = l == 0 ? kMsThreads / 32 : (l == 1 ? 8 : (l == 2 ? 12 : (l == 3 ? 14 : 15)));
+                float tot = 0.f;
+                for (int i = w0; i < w1; ++i) tot += wsum[l > 0][which][i];
+                atomicAdd(sums + which * 5 + l, (double)tot);
+            }
+        } else {
+            __syncthreads();
+            // ---- phase 3 / 4: dL/da_l(q) = blur(dmu)(q) + 2 a(q) blur(daa)(q) + b(q) blur(dab)(q)  (symmetric window)
+            CVAE_MS_FOR_TASKS({
+                const float* dm = Dm + lvl_off(lvl);
+                hpass<3, OUT>(S, t, w, Hm + lvl_off(lvl), [&](int idx, float* v) {
+                    v[0] = dm[idx]; v[1] = dm[kPyr + idx]; v[2] = dm[2 * kPyr + idx];
                 });
-                __syncthreads();
-                float* g = G + lvl_off(l);
-                vpass<3>(S, w, Hm, [&](int idx, const float* v) {
+            })
+            __syncthreads();
+            CVAE_MS_FOR_TASKS({
+                const float* a = A + lvl_off(lvl);
+                const float* b = Bp + lvl_off(lvl);
+                float* g = Dm + lvl_off(lvl);    // derivative map 0 is dead after phase 3
+                vpass<3, OUT>(S, t, w, Hm + lvl_off(lvl), [&](int idx, const float* v) {
                     g[idx] = v[0] + 2.f * a[idx] * v[1] + b[idx] * v[2];
                 });
-                __syncthreads();
-            }
-        }
-
-        if (BWD) {
+            })
+            __syncthreads();
             // chain through the average pools: each finer pixel inherits 1/4 of its parent's gradient
             const float go = grad_out ? __ldg(grad_out) : 1.f;
             float* dr = d_recon + (size_t)plane * 4096;
@@ -225,7 +263,7 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
 #pragma unroll
                 for (int l = 0; l < kLevels; ++l) {
                     const int S = lvl_size(l);
-                    acc += scale * G[lvl_off(l) + (r >> l) * (S + 1) + (c >> l)];
+                    acc += scale * Dm[lvl_off(l) + (r >> l) * (S + 1) + (c >> l)];
                     scale *= 0.25f;
                 }
                 dr[i] = acc * go;
@@ -233,6 +271,7 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
         }
     }
 }
+#undef CVAE_MS_FOR_TASKS
 
 // one block: KLD reduction + loss scalars + chain-rule coefficients
 __global__ void loss_finalize_kernel(int B, const float* __restrict__ ml, const double* __restrict__ sums,
@@ -284,7 +323,7 @@ __global__ void kld_bwd_kernel(int B, const float* __restrict__ ml, float kld_we
 using namespace cvae;
 
 static size_t ms_smem(bool bwd) {
-    return sizeof(float) * (size_t)(2 * kPyr + 5 * kMap + (bwd ? 3 * kMap + kPyr : 0));
+    return sizeof(float) * (size_t)(2 * kPyr + 5 * kPyr + (bwd ? 3 * kPyr : 0));
 }
 
 extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar,

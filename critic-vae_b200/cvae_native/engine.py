@@ -148,9 +148,29 @@ class VAEEngine:
         add("decin", L.PACK_DECIN, 0, 0, 0, 0, 0, W("decoder.decoder_input.weight"), W("decoder.decoder_input.bias"),
             torch.float32, 34 * 4096)
         self._jobs = (L.PackJob * len(jobs))(*jobs)
+        # data-gradient forms (keys ending in "g") are first needed by the backward pass
+        keys = list(self.packed.keys())
+        fwd = [j for j, k in zip(jobs, keys) if not k.endswith("g")]
+        bwd = [j for j, k in zip(jobs, keys) if k.endswith("g")]
+        self._jobs_fwd = (L.PackJob * len(fwd))(*fwd)
+        self._jobs_bwd = (L.PackJob * len(bwd))(*bwd)
+        self._bwd_packed = None
 
     def pack(self):
-        L.check(L.lib.cvae_pack_weights(self._jobs, len(self._jobs), L.stream_ptr()))
+        """Repack every operand form from the fp32 masters.  With a side stream the data-gradient forms are
+        packed beside the forward pass; backward() waits for them."""
+        if self.side_stream is None:
+            L.check(L.lib.cvae_pack_weights(self._jobs, len(self._jobs), L.stream_ptr()))
+            self._bwd_packed = None
+            return
+        fork = torch.cuda.Event()
+        fork.record()
+        self.side_stream.wait_event(fork)
+        with torch.cuda.stream(self.side_stream):
+            L.check(L.lib.cvae_pack_weights(self._jobs_bwd, len(self._jobs_bwd), L.stream_ptr()))
+            self._bwd_packed = torch.cuda.Event()
+            self._bwd_packed.record()
+        L.check(L.lib.cvae_pack_weights(self._jobs_fwd, len(self._jobs_fwd), L.stream_ptr()))
 
     def workspace(self, B, with_grad):
         key = (B, with_grad)
@@ -263,6 +283,9 @@ class VAEEngine:
         B, s = ws.B, L.stream_ptr()
         G = lambda n: self.view(n, g)
         self._side_used = False
+        if self._bwd_packed is not None:
+            torch.cuda.current_stream().wait_event(self._bwd_packed)
+            self._bwd_packed = None
         dm = "decoder.model."
         # D4 .. D1: up-sample-folded convs
         self._wgrad(g, dm + "12", kind=L.WGRAD_SHIFT_PHASE12, batch=B, height=32, width=32, cout=3, cin=32,

@@ -4,7 +4,7 @@ lines = [l for l in open(sys.argv[1]) if not l.startswith('==')]
 rows = list(csv.DictReader(lines))
 names = [r['Kernel Name'] for r in rows]
 packs = [i for i, n in enumerate(names) if 'pack_weights' in n]
-s, e = packs[-2], packs[-1]
+s, e = packs[-4], packs[-2]   # two pack launches (forward / data-gradient forms) per step
 agg, tot = collections.OrderedDict(), 0.0
 for r in rows[s:e]:
     n = re.sub(r'\(.*', '', r['Kernel Name']).replace('cvae::', '').replace('void ', '')
