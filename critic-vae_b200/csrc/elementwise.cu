@@ -53,9 +53,13 @@ __global__ void bn_finalize_kernel(int C, double count, int training, const doub
 
 __device__ __forceinline__ float act_fn(int act, float x) { return act == 0 ? fmaxf(x, 0.f) : tanhf(x); }
 
-// y = act(maxpool2x2(x*scale + shift)); x bf16 NHWC [B][H][W][C] -> y bf16 NHWC [B][H/2][W/2][C]
+// y = act(maxpool2x2(x*scale + shift)); x bf16 NHWC [B][H][W][C] -> y bf16 NHWC [B][H/2][W/2][C].
+// Training also saves what the backward needs per pooled element, so it does not have to redo the
+// normalisation of all four positions: the normalised value at the arg-max position (bf16) and the
+// arg-max position itself (2 bits per channel, one uint16 per 8-channel group).
 __global__ void bn_pool_act_fwd_kernel(int B, int H, int W, int C, int act, const uint4* __restrict__ x,
-                                       const float* __restrict__ ss, uint4* __restrict__ y) {
+                                       const float* __restrict__ ss, uint4* __restrict__ y,
+                                       uint4* __restrict__ xhat_max, uint16_t* __restrict__ argmax) {
     const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
     const long long total = (long long)B * Ho * Wo * cg;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -70,28 +74,45 @@ __global__ void bn_pool_act_fwd_kernel(int B, int H, int W, int C, int act, cons
         const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const size_t base = ((size_t)(n * H + 2 * ho) * W + 2 * wo) * cg + c8;
-        F8 m;
+        F8 m, xm;
+        uint32_t am = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const F8 v = unpack8(__ldg(x + base + (size_t)(q >> 1) * W * cg + (size_t)(q & 1) * cg));
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float b = fmaf(v.v[e], sc[e], sh[e]);
-                m.v[e] = q == 0 ? b : fmaxf(m.v[e], b);
+                if (q == 0 || b > m.v[e]) {   // first maximum wins, like nn.MaxPool2d
+                    m.v[e] = b;
+                    xm.v[e] = v.v[e];
+                    am = (am & ~(3u << (2 * e))) | ((uint32_t)q << (2 * e));
+                }
             }
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) m.v[e] = act_fn(act, m.v[e]);
         y[i] = pack8(m);
+        if (xhat_max != nullptr) {
+            const float4 m0 = __ldg((const float4*)(ss + 2 * C + c8 * 8)), m1 = __ldg((const float4*)(ss + 2 * C + c8 * 8 + 4));
+            const float4 i0 = __ldg((const float4*)(ss + 3 * C + c8 * 8)), i1 = __ldg((const float4*)(ss + 3 * C + c8 * 8 + 4));
+            const float mean[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            const float inv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xm.v[e] = (xm.v[e] - mean[e]) * inv[e];
+            xhat_max[i] = pack8(xm);
+            argmax[i] = (uint16_t)am;
+        }
     }
 }
 
-// Backward of act(maxpool(bn(x))).  PASS 0: per-channel sum(g), sum(g*xhat) with g routed to the
-// arg-max position;  PASS 1: dx = gamma*invstd*(g_full - sum(g)/n - xhat*sum(g*xhat)/n) at all 4
-// positions, plus dgamma/dbeta.
+// Backward of act(maxpool(bn(x))).
+// PASS 0 (pooled tensors only): per-channel sum(g), sum(g*xhat) with g = dy * act'(y) at the arg-max position.
+// PASS 1: dx = gamma*invstd*(g_full - sum(g)/n - xhat*sum(g*xhat)/n) at all 4 positions
+//            = [q == argmax] * (gi*g) + (c0 + c1*x_q)   with per-channel constants, plus dgamma/dbeta.
 template <int PASS>
 __global__ void bn_pool_act_bwd_kernel(int B, int H, int W, int C, int act, const uint4* __restrict__ x,
                                        const uint4* __restrict__ yact, const uint4* __restrict__ dy,
+                                       const uint4* __restrict__ xhat_max, const uint16_t* __restrict__ argmax,
                                        const float* __restrict__ ss, const float* __restrict__ gamma,
                                        double* sums, uint4* __restrict__ dx, float* dgamma, float* dbeta) {
     extern __shared__ float red[];  // PASS 0: [blockDim][16]
@@ -100,15 +121,16 @@ __global__ void bn_pool_act_bwd_kernel(int B, int H, int W, int C, int act, cons
     const int lanes = blockDim.x / cg;  // pixel lanes per block
     const long long npix = (long long)B * Ho * Wo;
     const double count = (double)B * H * W;
-    float sc[8], sh[8], mean[8], inv[8], k1[8], k2[8], gi[8];
+    float gi[8], k0[8], k1[8];
+    if (PASS == 1) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int c = c8 * 8 + e;
-        sc[e] = ss[c]; sh[e] = ss[C + c]; mean[e] = ss[2 * C + c]; inv[e] = ss[3 * C + c];
-        if (PASS == 1) {
-            k1[e] = (float)(sums[c] / count);
-            k2[e] = (float)(sums[C + c] / count);
-            gi[e] = gamma[c] * inv[e];
+        for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            const float mean = ss[2 * C + c], inv = ss[3 * C + c];
+            const float s1 = (float)(sums[c] / count), s2 = (float)(sums[C + c] / count);
+            gi[e] = gamma[c] * inv;
+            k1[e] = -gi[e] * s2 * inv;                 // coefficient of x_q
+            k0[e] = -gi[e] * s1 - k1[e] * mean;        // constant term
         }
     }
     float a1[8], a2[8];
@@ -116,41 +138,38 @@ __global__ void bn_pool_act_bwd_kernel(int B, int H, int W, int C, int act, cons
     for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.f;
 
     for (long long p = (long long)blockIdx.x * lanes + threadIdx.x / cg; p < npix; p += (long long)gridDim.x * lanes) {
-        const int wo = (int)(p % Wo);
-        const int ho = (int)((p / Wo) % Ho);
-        const int n = (int)(p / ((long long)Wo * Ho));
-        const size_t base = ((size_t)(n * H + 2 * ho) * W + 2 * wo) * cg + c8;
-        F8 xv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) xv[q] = unpack8(__ldg(x + base + (size_t)(q >> 1) * W * cg + (size_t)(q & 1) * cg));
         const F8 yv = unpack8(__ldg(yact + p * cg + c8));
         const F8 dv = unpack8(__ldg(dy + p * cg + c8));
-        F8 o[4];
+        float g[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int am = 0;
-            float best = fmaf(xv[0].v[e], sc[e], sh[e]);
+        for (int e = 0; e < 8; ++e)
+            g[e] = dv.v[e] * (act == 0 ? (yv.v[e] > 0.f ? 1.f : 0.f) : (1.f - yv.v[e] * yv.v[e]));
+        if (PASS == 0) {
+            const F8 xh = unpack8(__ldg(xhat_max + p * cg + c8));
 #pragma unroll
-            for (int q = 1; q < 4; ++q) {
-                const float b = fmaf(xv[q].v[e], sc[e], sh[e]);
-                if (b > best) { best = b; am = q; }
+            for (int e = 0; e < 8; ++e) {
+                a1[e] += g[e];
+                a2[e] = fmaf(g[e], xh.v[e], a2[e]);
             }
-            const float g = dv.v[e] * (act == 0 ? (yv.v[e] > 0.f ? 1.f : 0.f) : (1.f - yv.v[e] * yv.v[e]));
-            if (PASS == 0) {
-                const float xh = ((am == 0 ? xv[0].v[e] : am == 1 ? xv[1].v[e] : am == 2 ? xv[2].v[e] : xv[3].v[e]) - mean[e]) * inv[e];
-                a1[e] += g;
-                a2[e] += g * xh;
-            } else {
+        } else {
+            const int wo = (int)(p % Wo);
+            const int ho = (int)((p / Wo) % Ho);
+            const int n = (int)(p / ((long long)Wo * Ho));
+            const size_t base = ((size_t)(n * H + 2 * ho) * W + 2 * wo) * cg + c8;
+            const uint32_t am = argmax[p * cg + c8];
+            F8 xv[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float xh = (xv[q].v[e] - mean[e]) * inv[e];
-                    o[q].v[e] = gi[e] * ((q == am ? g : 0.f) - k1[e] - xh * k2[e]);
+            for (int q = 0; q < 4; ++q) xv[q] = unpack8(__ldg(x + base + (size_t)(q >> 1) * W * cg + (size_t)(q & 1) * cg));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                F8 o;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float r = fmaf(k1[e], xv[q].v[e], k0[e]);
+                    o.v[e] = (((am >> (2 * e)) & 3u) == (uint32_t)q) ? fmaf(gi[e], g[e], r) : r;
                 }
+                dx[base + (size_t)(q >> 1) * W * cg + (size_t)(q & 1) * cg] = pack8(o);
             }
-        }
-        if (PASS == 1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dx[base + (size_t)(q >> 1) * W * cg + (size_t)(q & 1) * cg] = pack8(o[q]);
         }
     }
     if (PASS == 0) {
@@ -268,24 +287,28 @@ extern "C" int cvae_bn_finalize(int channels, int64_t count, int training, const
 }
 
 extern "C" int cvae_bn_pool_act_fwd(int batch, int height, int width, int channels, int act,
-                                    const void* conv_out, const float* scale_shift, void* out, void* stream) {
+                                    const void* conv_out, const float* scale_shift, void* out, void* xhat_max,
+                                    void* argmax, void* stream) {
     CVAE_REQUIRE(batch > 0 && height % 2 == 0 && width % 2 == 0 && channels % 8 == 0, CVAE_EINVAL, "bn_pool_act_fwd: shape");
     CVAE_REQUIRE(conv_out && scale_shift && out, CVAE_EINVAL, "bn_pool_act_fwd: null tensor");
+    CVAE_REQUIRE((xhat_max == nullptr) == (argmax == nullptr), CVAE_EINVAL, "bn_pool_act_fwd: xhat_max and argmax go together");
     const long long items = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
     bn_pool_act_fwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
-        batch, height, width, channels, act, (const uint4*)conv_out, scale_shift, (uint4*)out);
+        batch, height, width, channels, act, (const uint4*)conv_out, scale_shift, (uint4*)out, (uint4*)xhat_max,
+        (uint16_t*)argmax);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
 
 extern "C" int cvae_bn_pool_act_bwd(int batch, int height, int width, int channels, int act,
                                     const void* conv_out, const void* act_out, const void* d_act,
+                                    const void* xhat_max, const void* argmax,
                                     const float* scale_shift, const float* gamma, double* sums,
                                     void* d_conv, float* dgamma, float* dbeta, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CVAE_REQUIRE(batch > 0 && height % 2 == 0 && width % 2 == 0 && channels % 8 == 0 && channels <= 256 &&
                      256 % (channels / 8) == 0, CVAE_EINVAL, "bn_pool_act_bwd: shape");
-    CVAE_REQUIRE(conv_out && act_out && d_act && scale_shift && gamma && sums && d_conv && dgamma && dbeta,
+    CVAE_REQUIRE(conv_out && act_out && d_act && xhat_max && argmax && scale_shift && gamma && sums && d_conv && dgamma && dbeta,
                  CVAE_EINVAL, "bn_pool_act_bwd: null tensor");
     CVAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * channels, stream));
     const int threads = 256, lanes = threads / (channels / 8);
@@ -295,11 +318,11 @@ extern "C" int cvae_bn_pool_act_bwd(int batch, int height, int width, int channe
     if (blocks > cap) blocks = cap;
     bn_pool_act_bwd_kernel<0><<<(int)blocks, threads, threads * 16 * sizeof(float), stream>>>(
         batch, height, width, channels, act, (const uint4*)conv_out, (const uint4*)act_out, (const uint4*)d_act,
-        scale_shift, gamma, sums, nullptr, nullptr, nullptr);
+        (const uint4*)xhat_max, (const uint16_t*)argmax, scale_shift, gamma, sums, nullptr, nullptr, nullptr);
     CVAE_LAUNCH_CHECK();
     bn_pool_act_bwd_kernel<1><<<(int)blocks, threads, 0, stream>>>(
         batch, height, width, channels, act, (const uint4*)conv_out, (const uint4*)act_out, (const uint4*)d_act,
-        scale_shift, gamma, sums, (uint4*)d_conv, dgamma, dbeta);
+        (const uint4*)xhat_max, (const uint16_t*)argmax, scale_shift, gamma, sums, (uint4*)d_conv, dgamma, dbeta);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }

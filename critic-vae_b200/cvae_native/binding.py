@@ -68,8 +68,8 @@ _SIGS = {
     "cvae_pack_elems": ([ctypes.POINTER(PackJob)], c_i64),
     "cvae_pack_weights": ([ctypes.POINTER(PackJob), c_int, P], c_int),
     "cvae_bn_finalize": ([c_int, c_i64, c_int, P, P, P, P, P, P, P, c_float, c_float, P, P], c_int),
-    "cvae_bn_pool_act_fwd": ([c_int, c_int, c_int, c_int, c_int, P, P, P, P], c_int),
-    "cvae_bn_pool_act_bwd": ([c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P], c_int),
+    "cvae_bn_pool_act_fwd": ([c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P], c_int),
+    "cvae_bn_pool_act_bwd": ([c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P], c_int),
     "cvae_fc_fwd": ([c_int, P, P, P, P, P, P], c_int),
     "cvae_fc_bwd": ([c_int, P, P, P, P, P, P, P, P, P], c_int),
     "cvae_decin_fwd": ([c_int, P, P, P, P], c_int),

@@ -59,6 +59,9 @@ class Workspace:
         self.B = B
         self.c = [e(B, h, h, co) for (_, co, h) in ENC]                 # bias-free conv outputs
         self.a = [e(B, h // 2, h // 2, co) for (_, co, h) in ENC]       # pooled + activated
+        if with_grad:   # saved by the BatchNorm/pool forward for its backward
+            self.xh = [e(B, h // 2, h // 2, co) for (_, co, h) in ENC]
+            self.am = [e(B, h // 2, h // 2, co // 8, dtype=torch.int16) for (_, co, h) in ENC]
         self.ml = e(B, 64, dtype=f32)
         self.zc = e(B, 33, dtype=f32)
         self.h0 = e(B, 4, 4, 256)
@@ -219,8 +222,10 @@ class VAEEngine:
                                            _ptr(self.view(bname + ".bias")), _ptr(self.view(cname + ".bias")),
                                            _ptr(self.running_mean[i]), _ptr(self.running_var[i]), _ptr(self.nbt[i]),
                                            BN_MOMENTUM, BN_EPS, _ptr(ws.ss[i]), s))
+            save = training and hasattr(ws, "xh")
             L.check(L.lib.cvae_bn_pool_act_fwd(B, h, h, co, L.ACT_TANH if i == 3 else L.ACT_RELU, _ptr(ws.c[i]),
-                                               _ptr(ws.ss[i]), _ptr(ws.a[i]), s))
+                                               _ptr(ws.ss[i]), _ptr(ws.a[i]), _ptr(ws.xh[i]) if save else None,
+                                               _ptr(ws.am[i]) if save else None, s))
         L.check(L.lib.cvae_fc_fwd(B, _ptr(ws.a[3]), _ptr(self.packed["fc"]), _ptr(self.view("encoder.fc_mu.bias")),
                                   _ptr(self.view("encoder.fc_var.bias")), _ptr(ws.ml), s))
         return ws.ml
@@ -314,7 +319,7 @@ class VAEEngine:
             ci, co, h = ENC[i]
             bname, cname = f"{em}{ENC_BN_IDX[i]}", f"{em}{ENC_CONV_IDX[i]}"
             L.check(L.lib.cvae_bn_pool_act_bwd(B, h, h, co, L.ACT_TANH if i == 3 else L.ACT_RELU, _ptr(ws.c[i]), _ptr(ws.a[i]),
-                                               _ptr(ws.g_a[i]), _ptr(ws.ss[i]), _ptr(self.view(bname + ".weight")),
+                                               _ptr(ws.g_a[i]), _ptr(ws.xh[i]), _ptr(ws.am[i]), _ptr(ws.ss[i]), _ptr(self.view(bname + ".weight")),
                                                _ptr(ws.bn_sums), _ptr(ws.g_c[i]), _ptr(G(bname + ".weight")),
                                                _ptr(G(bname + ".bias")), s))
             if i == 0:

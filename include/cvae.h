@@ -140,13 +140,17 @@ int cvae_pack_weights(const cvae_pack_job* jobs, int count, void* stream);
 int cvae_bn_finalize(int channels, int64_t count, int training, const double* stats, const float* gamma,
                      const float* beta, const float* conv_bias, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float momentum, float eps, float* scale_shift, void* stream);
+/* xhat_max (bf16 [B][H/2][W/2][C]: normalised value at the arg-max position) and argmax (uint16
+ * [B][H/2][W/2][C/8]: 2 bits per channel) are what the backward needs per pooled element; pass both or
+ * neither (NULL, NULL in evaluation). */
 int cvae_bn_pool_act_fwd(int batch, int height, int width, int channels, int act, const void* conv_out,
-                         const float* scale_shift, void* out, void* stream);
-/* conv_out bf16 [B][H][W][C]; act_out, d_act bf16 [B][H/2][W/2][C]; sums: [2][C] double scratch;
- * d_conv bf16 [B][H][W][C]; dgamma, dbeta fp32 [C] (overwritten). */
+                         const float* scale_shift, void* out, void* xhat_max, void* argmax, void* stream);
+/* conv_out bf16 [B][H][W][C]; act_out, d_act, xhat_max bf16 [B][H/2][W/2][C]; argmax as above; sums: [2][C]
+ * double scratch; d_conv bf16 [B][H][W][C]; dgamma, dbeta fp32 [C] (overwritten). */
 int cvae_bn_pool_act_bwd(int batch, int height, int width, int channels, int act, const void* conv_out,
-                         const void* act_out, const void* d_act, const float* scale_shift, const float* gamma,
-                         double* sums, void* d_conv, float* dgamma, float* dbeta, void* stream);
+                         const void* act_out, const void* d_act, const void* xhat_max, const void* argmax,
+                         const float* scale_shift, const float* gamma, double* sums, void* d_conv, float* dgamma,
+                         float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Linear layers: fc_mu || fc_var (vae_nets.py:98-99,105-109) and decoder_input (:137,143-144).

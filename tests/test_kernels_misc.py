@@ -101,7 +101,10 @@ def test_bn_pool_act_forward_and_backward(B, C, HW, act, training):
     L.check(L.lib.cvae_bn_finalize(C, B * HW * HW, int(training), ptr(stats), ptr(gam_d), ptr(bet_d), ptr(cb_d),
                                    ptr(rm_d), ptr(rv_d), ptr(nbt), 0.1, 1e-5, ptr(ss), L.stream_ptr()))
     y = torch.zeros(B, HW // 2, HW // 2, C, dtype=torch.bfloat16, device="cuda")
-    L.check(L.lib.cvae_bn_pool_act_fwd(B, HW, HW, C, act, ptr(x_dev), ptr(ss), ptr(y), L.stream_ptr()))
+    xh = torch.zeros(B, HW // 2, HW // 2, C, dtype=torch.bfloat16, device="cuda")
+    am = torch.zeros(B, HW // 2, HW // 2, C // 8, dtype=torch.int16, device="cuda")
+    L.check(L.lib.cvae_bn_pool_act_fwd(B, HW, HW, C, act, ptr(x_dev), ptr(ss), ptr(y), ptr(xh) if training else None,
+                                       ptr(am) if training else None, L.stream_ptr()))
     sync(L)
     np.testing.assert_allclose(from_nhwc(y).numpy(), y_ref.detach().float().numpy(), rtol=2 ** -7, atol=2e-3)
     if training:
@@ -116,7 +119,7 @@ def test_bn_pool_act_forward_and_backward(B, C, HW, act, training):
         dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
         # the kernel differentiates through ITS OWN forward output (bf16 y)
         dy_d = nhwc_bf16(dy)
-        L.check(L.lib.cvae_bn_pool_act_bwd(B, HW, HW, C, act, ptr(x_dev), ptr(y), ptr(dy_d), ptr(ss), ptr(gam_d),
+        L.check(L.lib.cvae_bn_pool_act_bwd(B, HW, HW, C, act, ptr(x_dev), ptr(y), ptr(dy_d), ptr(xh), ptr(am), ptr(ss), ptr(gam_d),
                                            ptr(sums), ptr(dconv), ptr(dg), ptr(db), L.stream_ptr()))
         sync(L)
         ref_dx = xr.grad.float()
