@@ -8,6 +8,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -15,39 +16,54 @@ namespace cvae {
 
 // ---- fc forward: ml[b][j] = sum_k a[b][k] * wfc[k][j] + bias[j];  a bf16 [B][4096] ---------------
 // A thread-block cluster of 8 CTAs shares one block of 16 rows: CTA r of the cluster owns the K slice
-// [512 r, 512 r + 512) and leaves its [16][64] partial in its own shared memory; after cluster.sync()
-// CTA r sums the eight partials of rows 2r, 2r+1 over distributed shared memory in rank order and adds
-// the bias -- one launch, no atomics, bit-reproducible.
+// [512 r, 512 r + 512), pulls its 128 KB weight slice and its 16 activation rows into shared memory with
+// bulk async copies (one mbarrier), and leaves its [16][64] partial in its own shared memory; after
+// cluster.sync() CTA r sums the eight partials of rows 2r, 2r+1 over distributed shared memory in rank
+// order and adds the bias -- one launch, no atomics, bit-reproducible.
 static constexpr int kFcRows = 16, kFcSplit = 8, kFcSlice = 4096 / kFcSplit;
+static constexpr size_t kFcSmem = (size_t)kFcSlice * 64 * 4 + (size_t)kFcRows * kFcSlice * 2;
 __global__ void __cluster_dims__(kFcSplit, 1, 1) __launch_bounds__(256)
 fc_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restrict__ wfc,
-              const float* __restrict__ bmu, const float* __restrict__ bvar, float* __restrict__ ml) {
-    __shared__ __align__(16) float sa[kFcSlice][kFcRows];   // [k][row] of this CTA's K slice (32 KB)
+              const float* __restrict__ bmu, const float* __restrict__ bvar, float* __restrict__ ml, int* fault) {
+    extern __shared__ __align__(128) uint8_t fc_smem[];
+    float* sw = reinterpret_cast<float*>(fc_smem);                                        // [512][64]
+    uint32_t* sa = reinterpret_cast<uint32_t*>(fc_smem + (size_t)kFcSlice * 64 * 4);      // [16][256] bf16 pairs
     __shared__ float part[kFcRows][64];
+    __shared__ uint64_t bar;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int b0 = (blockIdx.x / kFcSplit) * kFcRows, k0 = rank * kFcSlice;
-    for (int t = threadIdx.x; t < kFcSlice * (kFcRows / 4); t += 256) {
-        const int k = t % kFcSlice, rq = t / kFcSlice;
-        float4 v;
-        float* pv = &v.x;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = b0 + rq * 4 + i;
-            pv[i] = r < B ? __bfloat162float(a[(size_t)r * 4096 + k0 + k]) : 0.f;
-        }
-        *reinterpret_cast<float4*>(&sa[k][rq * 4]) = v;
-    }
+    const int rows = min(kFcRows, B - b0);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (int i = threadIdx.x; i < (kFcRows - rows) * (kFcSlice / 2); i += 256) sa[rows * (kFcSlice / 2) + i] = 0u;
     __syncthreads();
-    const int j = threadIdx.x & 63, rq = threadIdx.x >> 6;   // a warp shares rq: the float4 read is a broadcast
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            mbar_expect_tx(&bar, (uint32_t)(kFcSlice * 64 * 4 + rows * kFcSlice * 2));
+            for (int c = 0; c < 8; ++c)
+                bulk_g2s(fc_smem + (size_t)c * 16384, reinterpret_cast<const uint8_t*>(wfc + (size_t)k0 * 64) + (size_t)c * 16384, 16384, &bar);
+            for (int r = 0; r < rows; ++r)
+                bulk_g2s(sa + r * (kFcSlice / 2), a + (size_t)(b0 + r) * 4096 + k0, kFcSlice * 2, &bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&bar, 0, fault);
+    const int j = threadIdx.x & 63, rq = threadIdx.x >> 6;   // a warp shares rq: the activation reads are broadcasts
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* w = wfc + (size_t)k0 * 64 + j;
-#pragma unroll 8
-    for (int k = 0; k < kFcSlice; ++k) {
-        const float wv = __ldg(w + (size_t)k * 64);
-        const float4 x = *reinterpret_cast<const float4*>(&sa[k][rq * 4]);
-        acc[0] = fmaf(wv, x.x, acc[0]); acc[1] = fmaf(wv, x.y, acc[1]);
-        acc[2] = fmaf(wv, x.z, acc[2]); acc[3] = fmaf(wv, x.w, acc[3]);
+#pragma unroll 2
+    for (int k8 = 0; k8 < kFcSlice / 8; ++k8) {
+        uint4 xr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xr[i] = *reinterpret_cast<const uint4*>(sa + (rq * 4 + i) * (kFcSlice / 2) + k8 * 4);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const float wv = sw[(k8 * 8 + kk) * 64 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t u = (kk >> 1) == 0 ? xr[i].x : ((kk >> 1) == 1 ? xr[i].y : ((kk >> 1) == 2 ? xr[i].z : xr[i].w));
+                acc[i] = fmaf(wv, (kk & 1) ? bf16_hi(u) : bf16_lo(u), acc[i]);
+            }
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) part[rq * 4 + i][j] = acc[i];
@@ -168,43 +184,65 @@ __global__ void decin_fwd_kernel(int B, const float* __restrict__ zc, const floa
 }
 
 // ---- decoder_input backward (data): dzc[b][i] = sum_k' dh[b][k'] * wdec[i][k'] ----------------------
-// block = 4 batch rows staged in shared memory as bf16; warp w owns outputs i = w, w+8, ...; every
-// weight value loaded from L2 is used for the 4 rows.
-static constexpr int kDdRows = 4;
-__global__ void __launch_bounds__(256) decin_bwd_data_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* __restrict__ wdec,
-                                                             float* __restrict__ dzc) {
-    __shared__ __align__(16) uint32_t sdh[kDdRows][2048];   // bf16 pairs
-    const int b0 = blockIdx.x * kDdRows;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int t = threadIdx.x; t < kDdRows * 512; t += 256) {
-        const int r = t >> 9, q = t & 511;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (b0 + r < B) v = __ldg(reinterpret_cast<const uint4*>(dh + (size_t)(b0 + r) * 4096) + q);
-        *reinterpret_cast<uint4*>(&sdh[r][q * 4]) = v;
-    }
+// Same shape of solution as fc_fwd_kernel: a cluster of 8 CTAs splits K for a block of 16 batch rows, operands
+// arrive by bulk async copies, partial [16][33] tiles are combined over distributed shared memory in rank order.
+static constexpr int kDdRows = 16, kDdSplit = 8, kDdSlice = 4096 / kDdSplit, kDdWStride = kDdSlice + 4;  // floats; +4 keeps rows 16 B aligned
+static constexpr size_t kDdSmem = (size_t)33 * kDdWStride * 4 + (size_t)kDdRows * kDdSlice * 2;
+__global__ void __cluster_dims__(kDdSplit, 1, 1) __launch_bounds__(256)
+decin_bwd_data_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* __restrict__ wdec, float* __restrict__ dzc, int* fault) {
+    extern __shared__ __align__(128) uint8_t dd_smem[];
+    float* sw = reinterpret_cast<float*>(dd_smem);                                            // [33][516]
+    uint32_t* sd = reinterpret_cast<uint32_t*>(dd_smem + (size_t)33 * kDdWStride * 4);         // [16][256] bf16 pairs
+    __shared__ float part[kDdRows][33];
+    __shared__ uint64_t bar;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = (blockIdx.x / kDdSplit) * kDdRows, k0 = rank * kDdSlice;
+    const int rows = min(kDdRows, B - b0);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (int i = threadIdx.x; i < (kDdRows - rows) * (kDdSlice / 2); i += 256) sd[rows * (kDdSlice / 2) + i] = 0u;
     __syncthreads();
-    for (int i = warp; i < 33; i += 8) {
-        float acc[kDdRows];
-#pragma unroll
-        for (int r = 0; r < kDdRows; ++r) acc[r] = 0.f;
-        const float2* w = reinterpret_cast<const float2*>(wdec + (size_t)i * 4096);
-#pragma unroll 4
-        for (int t = 0; t < 64; ++t) {
-            const int kk = t * 32 + lane;   // pair index
-            const float2 wv = __ldg(w + kk);
-#pragma unroll
-            for (int r = 0; r < kDdRows; ++r) {
-                const uint32_t u = sdh[r][kk];
-                acc[r] = fmaf(bf16_lo(u), wv.x, acc[r]);
-                acc[r] = fmaf(bf16_hi(u), wv.y, acc[r]);
-            }
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            mbar_expect_tx(&bar, (uint32_t)(33 * kDdSlice * 4 + rows * kDdSlice * 2));
+            for (int i = 0; i < 33; ++i) bulk_g2s(sw + i * kDdWStride, wdec + (size_t)i * 4096 + k0, kDdSlice * 4, &bar);
+            for (int r = 0; r < rows; ++r) bulk_g2s(sd + r * (kDdSlice / 2), dh + (size_t)(b0 + r) * 4096 + k0, kDdSlice * 2, &bar);
         }
-#pragma unroll
-        for (int r = 0; r < kDdRows; ++r) {
-            const float sacc = warp_sum(acc[r]);
-            if (lane == 0 && b0 + r < B) dzc[(size_t)(b0 + r) * 33 + i] = sacc;
+        __syncwarp();
+    }
+    mbar_wait(&bar, 0, fault);
+    // thread -> row r = tid / 16, outputs i = ig, ig + 16 (and 32 for ig == 0)
+    const int r = threadIdx.x >> 4, ig = threadIdx.x & 15;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    const float* w0 = sw + ig * kDdWStride;
+    const float* w1 = sw + (ig + 16) * kDdWStride;
+    const float* w2 = sw + 32 * kDdWStride;
+    const uint32_t* xr = sd + r * (kDdSlice / 2);
+#pragma unroll 4
+    for (int kp = 0; kp < kDdSlice / 2; ++kp) {
+        const uint32_t u = xr[kp];
+        const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+        const float2 a = *reinterpret_cast<const float2*>(w0 + 2 * kp);
+        const float2 b = *reinterpret_cast<const float2*>(w1 + 2 * kp);
+        acc0 = fmaf(x0, a.x, acc0); acc0 = fmaf(x1, a.y, acc0);
+        acc1 = fmaf(x0, b.x, acc1); acc1 = fmaf(x1, b.y, acc1);
+        if (ig == 0) {
+            const float2 c = *reinterpret_cast<const float2*>(w2 + 2 * kp);
+            acc2 = fmaf(x0, c.x, acc2); acc2 = fmaf(x1, c.y, acc2);
         }
     }
+    part[r][ig] = acc0;
+    part[r][ig + 16] = acc1;
+    if (ig == 0) part[r][32] = acc2;
+    cluster.sync();
+    if (threadIdx.x < 66) {
+        const int rr = rank * 2 + threadIdx.x / 33, i = threadIdx.x % 33;
+        float sacc = 0.f;
+#pragma unroll
+        for (int q = 0; q < kDdSplit; ++q) sacc += cluster.map_shared_rank(&part[0][0], q)[rr * 33 + i];
+        if (b0 + rr < B) dzc[(size_t)(b0 + rr) * 33 + i] = sacc;
+    }
+    cluster.sync();
 }
 
 // ---- decoder_input backward (weights + bias), reference layout dW [4096 k][33], db [4096 k] ---------
@@ -248,7 +286,15 @@ extern "C" int cvae_fc_fwd(int batch, const void* act, const float* wfc, const f
                            const float* bias_var, float* mu_logvar, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CVAE_REQUIRE(batch > 0 && act && wfc && bias_mu && bias_var && mu_logvar, CVAE_EINVAL, "fc_fwd: bad argument");
-    fc_fwd_kernel<<<((batch + kFcRows - 1) / kFcRows) * kFcSplit, 256, 0, stream>>>(batch, (const __nv_bfloat16*)act, wfc, bias_mu, bias_var, mu_logvar);
+    static thread_local bool configured = false;
+    if (!configured) {
+        CVAE_CUDA(cudaFuncSetAttribute(fc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmem));
+        configured = true;
+    }
+    int* fault = fault_flag();
+    CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "fc_fwd: fault flag unavailable");
+    fc_fwd_kernel<<<((batch + kFcRows - 1) / kFcRows) * kFcSplit, 256, kFcSmem, stream>>>(batch, (const __nv_bfloat16*)act, wfc, bias_mu,
+                                                                                          bias_var, mu_logvar, fault);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -256,12 +302,18 @@ extern "C" int cvae_fc_fwd(int batch, const void* act, const float* wfc, const f
 extern "C" int cvae_fc_bwd(int batch, const float* d_mu_logvar, const void* act, const float* wfc,
                            void* d_act, float* dw_mu, float* dw_var, float* db_mu, float* db_var, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    CVAE_REQUIRE(batch > 0 && d_mu_logvar && act && wfc && d_act && dw_mu && dw_var && db_mu && db_var, CVAE_EINVAL,
-                 "fc_bwd: bad argument");
-    fc_bwd_data_kernel<<<dim3((batch + 7) / 8, 4), 256, 0, stream>>>(batch, d_mu_logvar, wfc, (__nv_bfloat16*)d_act);
-    CVAE_LAUNCH_CHECK();
-    fc_bwd_weight_kernel<<<4096 / 32, 256, 0, stream>>>(batch, d_mu_logvar, (const __nv_bfloat16*)act, dw_mu, dw_var, db_mu, db_var);
-    CVAE_LAUNCH_CHECK();
+    const bool want_w = dw_mu || dw_var || db_mu || db_var;
+    CVAE_REQUIRE(batch > 0 && d_mu_logvar && (d_act || want_w), CVAE_EINVAL, "fc_bwd: bad argument");
+    if (d_act) {
+        CVAE_REQUIRE(wfc != nullptr, CVAE_EINVAL, "fc_bwd: data gradient needs the packed weights");
+        fc_bwd_data_kernel<<<dim3((batch + 7) / 8, 4), 256, 0, stream>>>(batch, d_mu_logvar, wfc, (__nv_bfloat16*)d_act);
+        CVAE_LAUNCH_CHECK();
+    }
+    if (want_w) {
+        CVAE_REQUIRE(act && dw_mu && dw_var && db_mu && db_var, CVAE_EINVAL, "fc_bwd: weight gradient outputs go together");
+        fc_bwd_weight_kernel<<<4096 / 32, 256, 0, stream>>>(batch, d_mu_logvar, (const __nv_bfloat16*)act, dw_mu, dw_var, db_mu, db_var);
+        CVAE_LAUNCH_CHECK();
+    }
     return CVAE_OK;
 }
 
@@ -275,10 +327,24 @@ extern "C" int cvae_decin_fwd(int batch, const float* z_pred, const float* wdec,
 extern "C" int cvae_decin_bwd(int batch, const void* d_out, const float* z_pred, const float* wdec,
                               float* d_z_pred, float* dw, float* db, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    CVAE_REQUIRE(batch > 0 && d_out && z_pred && wdec && d_z_pred && dw && db, CVAE_EINVAL, "decin_bwd: bad argument");
-    decin_bwd_data_kernel<<<(batch + kDdRows - 1) / kDdRows, 256, 0, stream>>>(batch, (const __nv_bfloat16*)d_out, wdec, d_z_pred);
-    CVAE_LAUNCH_CHECK();
-    decin_bwd_weight_kernel<<<4096 / 32, 256, 0, stream>>>(batch, (const __nv_bfloat16*)d_out, z_pred, dw, db);
-    CVAE_LAUNCH_CHECK();
+    CVAE_REQUIRE(batch > 0 && d_out && (d_z_pred || dw || db), CVAE_EINVAL, "decin_bwd: bad argument");
+    if (d_z_pred) {
+        CVAE_REQUIRE(wdec != nullptr, CVAE_EINVAL, "decin_bwd: data gradient needs the packed weights");
+        static thread_local bool configured = false;
+        if (!configured) {
+            CVAE_CUDA(cudaFuncSetAttribute(decin_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDdSmem));
+            configured = true;
+        }
+        int* fault = fault_flag();
+        CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "decin_bwd: fault flag unavailable");
+        decin_bwd_data_kernel<<<((batch + kDdRows - 1) / kDdRows) * kDdSplit, 256, kDdSmem, stream>>>(
+            batch, (const __nv_bfloat16*)d_out, wdec, d_z_pred, fault);
+        CVAE_LAUNCH_CHECK();
+    }
+    if (dw || db) {
+        CVAE_REQUIRE(z_pred && dw && db, CVAE_EINVAL, "decin_bwd: weight gradient outputs go together");
+        decin_bwd_weight_kernel<<<4096 / 32, 256, 0, stream>>>(batch, (const __nv_bfloat16*)d_out, z_pred, dw, db);
+        CVAE_LAUNCH_CHECK();
+    }
     return CVAE_OK;
 }

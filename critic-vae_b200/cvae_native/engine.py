@@ -281,6 +281,18 @@ class VAEEngine:
             L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()))
         self._side_used = True
 
+    def _leaf(self, launch):
+        """Run a parameter-gradient launch (a leaf of the backward pass) on the side stream when there is one."""
+        if self.side_stream is None or self.profile is not None:
+            launch(L.stream_ptr())
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.side_stream.wait_event(ev)
+        with torch.cuda.stream(self.side_stream):
+            launch(L.stream_ptr())
+        self._side_used = True
+
     def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None):
         """Gradients of every parameter into the flat buffer `g` (default self.gflat), given the
         gradients of the loss w.r.t. recon / mu / logvar.  Mirrors autograd through vae_nets.py:14-19."""
@@ -308,12 +320,15 @@ class VAEEngine:
         self._wgrad(g, dm + "0", kind=L.WGRAD_5X5, batch=B, height=4, width=4, cout=128, cin=256, x=ws.h0, dy=ws.g_d[0])
         self._conv(batch=B, height=4, width=4, ksize=5, src_channels=128, n_total=256, loader=L.LOAD_NHWC,
                    epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_d[0], wpack=self.packed["D0g"], out=ws.g_h0)
-        L.check(L.lib.cvae_decin_bwd(B, _ptr(ws.g_h0), _ptr(ws.zc), _ptr(self.packed["decin"]), _ptr(ws.dzc),
-                                     _ptr(G("decoder.decoder_input.weight")), _ptr(G("decoder.decoder_input.bias")), s))
+        self._leaf(lambda st: L.check(L.lib.cvae_decin_bwd(B, _ptr(ws.g_h0), _ptr(ws.zc), None, None,
+                                                           _ptr(G("decoder.decoder_input.weight")),
+                                                           _ptr(G("decoder.decoder_input.bias")), st)))
+        L.check(L.lib.cvae_decin_bwd(B, _ptr(ws.g_h0), None, _ptr(self.packed["decin"]), _ptr(ws.dzc), None, None, s))
         L.check(L.lib.cvae_latent_bwd(B, _ptr(ws.ml), _ptr(eps), _ptr(ws.dzc), _ptr(d_mu), _ptr(d_lv), _ptr(ws.dml), s))
-        L.check(L.lib.cvae_fc_bwd(B, _ptr(ws.dml), _ptr(ws.a[3]), _ptr(self.packed["fc"]), _ptr(ws.g_a[3]),
-                                  _ptr(G("encoder.fc_mu.weight")), _ptr(G("encoder.fc_var.weight")),
-                                  _ptr(G("encoder.fc_mu.bias")), _ptr(G("encoder.fc_var.bias")), s))
+        self._leaf(lambda st: L.check(L.lib.cvae_fc_bwd(B, _ptr(ws.dml), _ptr(ws.a[3]), None, None,
+                                                        _ptr(G("encoder.fc_mu.weight")), _ptr(G("encoder.fc_var.weight")),
+                                                        _ptr(G("encoder.fc_mu.bias")), _ptr(G("encoder.fc_var.bias")), st)))
+        L.check(L.lib.cvae_fc_bwd(B, _ptr(ws.dml), None, _ptr(self.packed["fc"]), _ptr(ws.g_a[3]), None, None, None, None, s))
         em = "encoder.model."
         for i in (3, 2, 1, 0):
             ci, co, h = ENC[i]

@@ -156,7 +156,9 @@ int cvae_bn_pool_act_bwd(int batch, int height, int width, int channels, int act
  * Linear layers: fc_mu || fc_var (vae_nets.py:98-99,105-109) and decoder_input (:137,143-144).
  * act: bf16 NHWC-flattened bottleneck [B][4096]; mu_logvar fp32 [B][64] (mu | logvar);
  * wfc / wdec are the CVAE_PACK_FC / CVAE_PACK_DECIN outputs; gradients are written in the
- * reference's parameter layouts.
+ * reference's parameter layouts.  In the backward calls either half may be skipped by passing NULL
+ * for its outputs (d_act / d_z_pred = data gradient; dw*, db* = parameter gradients), so the two
+ * halves can run on different streams.
  * ---------------------------------------------------------------------------------------------- */
 int cvae_fc_fwd(int batch, const void* act, const float* wfc, const float* bias_mu, const float* bias_var,
                 float* mu_logvar, void* stream);

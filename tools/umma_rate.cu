@@ -407,6 +407,21 @@ static void run_mn(const char* name, RateArgs p, int grid) {
 
 int main(int argc, char** argv) {
     const uint32_t reps = 960;
+    if (argc > 1 && !strcmp(argv[1], "real")) {
+        // mode bit 0: three warps hammer shared memory with st.shared.v4; bit 1: one warp streams 8 KB bulk copies
+        uint8_t* gsrc;
+        cudaMalloc(&gsrc, 2 << 20);
+        cudaMemset(gsrc, 0, 2 << 20);
+        for (int grid : {1, 148})
+            for (uint32_t mode : {0u, 1u, 2u, 3u}) {
+                run_real<128, 1>(grid, mode, gsrc);
+                run_real<128, 2>(grid, mode, gsrc);
+                run_real<64, 2>(grid, mode, gsrc);
+                run_real<64, 4>(grid, mode, gsrc);
+                run_real<32, 4>(grid, mode, gsrc);
+            }
+        return 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "mn")) {
         // weight-gradient layouts: operands MN-major (16 B = 8 M/N elements, pixel slots = K), LBO 128,
         // SBO = plane stride (plane = 256 pixel slots here); the start address advances 256 B (16 pixels) per MMA
