@@ -308,6 +308,42 @@ __device__ __forceinline__ void mma_role(const ConvArgs& a, PipeBars& bars, uint
     }
 }
 
+// MMA role for the 8-channel source of encoder conv 0 (CVAE_KTAB_PAIR8): 13 K steps cover the 25 taps two at a
+// time -- the two 8-channel halves of a K = 16 step are the same plane read one pixel (LBO 16 B) or one row
+// (LBO PW * 16 B) apart.  The 13 KB weight block is loaded once and stays resident.
+template <int N, int TM>
+__device__ __forceinline__ void mma_role_pair8(const ConvArgs& a, PipeBars& bars, uint32_t tmem_base, uint32_t pbuf16, uint32_t wring_addr,
+                                               int n_items) {
+    const uint32_t idesc = umma_idesc_bf16(N, kMajorK, kMajorK);
+    const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
+    const uint32_t b_lo0 = ((wring_addr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ab = it & 1u, buf = it & 1u;
+        mbar_wait(&bars.acc_empty[ab], ((it >> 1) & 1u) ^ 1u, a.fault);
+        mbar_wait(&bars.p_full[buf], (it >> 1) & 1u, a.fault);
+        if (it == 0) mbar_wait(&bars.w_full[0], 0, a.fault);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + ab * (uint32_t)(TM * N);
+        const uint32_t a_buf = pbuf16 + ((buf * (uint32_t)a.buf_bytes) >> 4) + (uint32_t)a.halo;
+#pragma unroll
+        for (int i = 0; i < 13; ++i) {
+            int off;          // first tap of the pair, in pixels relative to the output pixel
+            uint32_t lbo16;   // distance to the second tap, in 16-byte units
+            if (i < 10) { off = ((i >> 1) - 2) * a.PW + ((i & 1) * 2 - 2); lbo16 = 1u; }
+            else if (i < 12) { off = ((i - 10) * 2 - 2) * a.PW + 2; lbo16 = (uint32_t)a.PW; }
+            else { off = 2 * a.PW + 2; lbo16 = 1u; }
+            const uint32_t a_lo = (uint32_t)((int)a_buf + off) | (lbo16 << 16);
+            const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(i * N * 2));
+#pragma unroll
+            for (int t = 0; t < TM; ++t)
+                umma_bf16(acc + (uint32_t)(t * N), ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(t * 128)), db, idesc, i > 0 ? 1u : 0u);
+        }
+        umma_commit(&bars.p_empty[buf]);
+        umma_commit(&bars.acc_full[ab]);
+    }
+}
+
 template <int N, int KW, int TM>
 __device__ __forceinline__ void mma_role_ks(const ConvArgs& a, PipeBars& bars, uint32_t tmem_base, uint32_t pbuf16,
                                             uint32_t wring_addr, int n_items, uint32_t stage_bytes) {
@@ -398,6 +434,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvAr
         // ================================ MMA issuer (highest warp id: the scheduler favours it) ==============================================
         if (elect_one()) {
             const uint32_t pbuf16 = (smem_u32(pbuf) & 0x3FFFFu) >> 4, wring_addr = smem_u32(wring);
+            if constexpr (LOADER == CVAE_LOAD_NCHW3) {
+                switch (a.tm) {
+                    case 2: mma_role_pair8<N, 2>(a, bars, tmem_base, pbuf16, wring_addr, n_items); break;
+                    case 4: mma_role_pair8<N, 4>(a, bars, tmem_base, pbuf16, wring_addr, n_items); break;
+                    case 8: mma_role_pair8<N, 8>(a, bars, tmem_base, pbuf16, wring_addr, n_items); break;
+                    default: mma_role_pair8<N, 1>(a, bars, tmem_base, pbuf16, wring_addr, n_items); break;
+                }
+            } else
             switch (a.tm) {
                 case 1: mma_role_ks<N, KW, 1>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes); break;
                 case 2: mma_role_ks<N, KW, 2>(a, bars, tmem_base, pbuf16, wring_addr, n_items, stage_bytes); break;
@@ -465,9 +509,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvAr
                 if (alive) alive = mbar_wait(&p_empty[buf], ((p >> 1) & 1u) ^ 1u, a.fault);
                 t_pe += clock64() - tq;
                 tq = clock64();
-                if (!(a.dbg_flags & 2) || p < 2)
-                fill_planes_async<LOADER>(a.ps, a.dPW, a.dIH, pbuf + (size_t)buf * a.buf_bytes, a.plane_stride, v0 - a.halo, a.L,
-                                          cg * a.planes, a.planes, ptid, kProducerThreads);
+                if (!(a.dbg_flags & 2) || p < 2) {
+                    if constexpr (LOADER == CVAE_LOAD_NHWC || LOADER == CVAE_LOAD_S2D)
+                        fill_planes_async<LOADER>(a.ps, a.dPW, a.dIH, pbuf + (size_t)buf * a.buf_bytes, a.plane_stride, v0 - a.halo, a.L,
+                                                  cg * a.planes, a.planes, ptid, kProducerThreads);
+                    else   // fp32 NCHW sources are converted by the producer threads themselves
+                        fill_planes<LOADER>(a.ps, pbuf + (size_t)buf * a.buf_bytes, a.plane_stride, v0 - a.halo, a.L, ptid, kProducerThreads);
+                }
                 cp_async_wait_all();
                 fence_proxy_async();
                 mbar_arrive(&p_full[buf]);
@@ -737,7 +785,8 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     a.ps = PlaneSrc{a.B, a.H, a.W, a.pad, a.PW, a.IH, all_planes,
                     (d->loader == CVAE_LOAD_S2D) ? d->src_channels / 4 : d->src_channels, 0, d->src, d->src2};
 
-    if (d->loader == CVAE_LOAD_NCHW3 || d->loader == CVAE_LOAD_S2D_NCHW3_DTANH) return conv_sequential(d, a, stream);
+    if (getenv("CVAE_SEQ_FP32") && (d->loader == CVAE_LOAD_NCHW3 || d->loader == CVAE_LOAD_S2D_NCHW3_DTANH))
+        return conv_sequential(d, a, stream);
 
     // ---- tiling policy of the pipelined kernel -----------------------------------------------------
     const long total_v = (long)a.B * a.IH * a.PW - (long)a.pad * a.PW;  // pixels from first to last valid row
@@ -782,7 +831,9 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     while (tm > 1 && 2 * tm * N > 512) --tm;   // two accumulator sets must fit the 512 TMEM columns
     if (tm == 5) tm = 4;
     if (tm == 7) tm = 6;
-    CVAE_REQUIRE(d->ktab == CVAE_KTAB_GENERIC, CVAE_EINVAL, "conv_gemm: the pipelined kernel needs the generic K order");
+    const bool pair8 = d->ktab == CVAE_KTAB_PAIR8;
+    CVAE_REQUIRE(pair8 == (d->loader == CVAE_LOAD_NCHW3), CVAE_EINVAL, "conv_gemm: the paired-tap K order goes with the frame loader");
+    if (pair8) tm = tm >= 8 ? 8 : (tm >= 4 ? 4 : (tm >= 2 ? 2 : 1));
     CVAE_REQUIRE(tm >= 1 && 2 * tm * N <= 512, CVAE_EINVAL, "conv_gemm: tm %d x n_block %d exceeds tensor memory", tm, N);
     a.n_blocks = d->n_total / N;
     a.tm = tm;
@@ -802,6 +853,7 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     a.ksps = a.kgroup;
     for (int c = a.kgroup; c <= run; c += a.kgroup)
         if (run % c == 0 && a.kpg % c == 0 && (size_t)c * N * 32 <= kStageBytesMax) a.ksps = c;
+    if (pair8) a.ksps = a.kgroup = 13;   // one resident 13-step block
     const size_t stage_bytes = (size_t)a.ksps * N * 32;
     const long budget = (long)kDynSmemMax - 2 * (long)a.buf_bytes - (long)a.kpg * 8 - 64;
     CVAE_REQUIRE(budget >= (long)(2 * stage_bytes), CVAE_EINVAL, "conv_gemm: shape does not fit shared memory");
@@ -822,6 +874,8 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     CVAE_CASE(CVAE_LOAD_NHWC, CVAE_EPI_PHASE_BIAS_TANH, 16, 3)
     CVAE_CASES(CVAE_LOAD_NHWC, CVAE_EPI_PLAIN, 5)
     CVAE_CASES(CVAE_LOAD_S2D, CVAE_EPI_MASK, 3)
+    CVAE_CASE(CVAE_LOAD_NCHW3, CVAE_EPI_STATS, 32, 5)
+    CVAE_CASE(CVAE_LOAD_S2D_NCHW3_DTANH, CVAE_EPI_MASK, 32, 3)
 #undef CVAE_CASES
 #undef CVAE_CASE
     set_error("conv_gemm: no kernel for loader %d epilogue %d N %d", d->loader, d->epilogue, N);

@@ -96,11 +96,18 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         eng.check_fault()
-        g_front, g_back = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_front):
-            self._front(from_u8)
-        with torch.cuda.graph(g_back):
-            self._back()
+        # One graph for the whole step (the NCCL all-reduce is capturable); CVAE_SPLIT_GRAPH=1 keeps the all-reduce
+        # outside, between a forward/backward graph and an Adam graph.
+        if os.environ.get("CVAE_SPLIT_GRAPH") is None:
+            g_front, g_back = torch.cuda.CUDAGraph(), None
+            with torch.cuda.graph(g_front):
+                self._eager(from_u8)
+        else:
+            g_front, g_back = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_front):
+                self._front(from_u8)
+            with torch.cuda.graph(g_back):
+                self._back()
         # undo the warm-up step
         eng.flat.copy_(keep[0]); eng.step.copy_(keep[1])
         n = len(eng.running_mean)
@@ -134,7 +141,8 @@ class TrainStep:
         if gs is None:
             gs = self._graphs[from_u8] = self._capture(from_u8)
         gs[0].replay()
-        if self.world > 1:
-            torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
-        gs[1].replay()
+        if gs[1] is not None:
+            if self.world > 1:
+                torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
+            gs[1].replay()
         return self.losses

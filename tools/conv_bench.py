@@ -17,6 +17,8 @@ bf = torch.bfloat16
 
 # name, H, ksize, src_channels, n_total, loader, epilogue, real MACs per output pixel row (for TFLOP/s)
 LAYERS = [
+    ("E0f", 64, 5, 8, 32, L.LOAD_NCHW3, L.EPI_STATS),
+    ("D4g", 32, 3, 16, 32, L.LOAD_S2D_NCHW3_DTANH, L.EPI_MASK),
     ("E1f", 32, 5, 32, 64, L.LOAD_NHWC, L.EPI_STATS),
     ("E2f", 16, 5, 64, 128, L.LOAD_NHWC, L.EPI_STATS),
     ("E3f", 8, 5, 128, 256, L.LOAD_NHWC, L.EPI_STATS),
@@ -36,8 +38,15 @@ LAYERS = [
 
 
 def bench(name, H, k, C, N, loader, epi, tm=0, nblk=0, iters=20):
-    ksteps = L.lib.cvae_conv_ksteps(k, C, L.KTAB_GENERIC)
-    if loader == L.LOAD_S2D:
+    ktab = L.KTAB_PAIR8 if loader == L.LOAD_NCHW3 else L.KTAB_GENERIC
+    ksteps = L.lib.cvae_conv_ksteps(k, C, ktab)
+    src2 = None
+    if loader == L.LOAD_NCHW3:
+        src = torch.rand(B, 3, H, H, device=dev)
+    elif loader == L.LOAD_S2D_NCHW3_DTANH:
+        src = torch.randn(B, 3, 2 * H, 2 * H, device=dev)
+        src2 = torch.rand(B, 3, 2 * H, 2 * H, device=dev)
+    elif loader == L.LOAD_S2D:
         src = torch.randn(B, 2 * H, 2 * H, C // 4, device=dev).to(bf)
     else:
         src = torch.randn(B, H, H, C, device=dev).to(bf)
@@ -52,7 +61,8 @@ def bench(name, H, k, C, N, loader, epi, tm=0, nblk=0, iters=20):
     act = torch.randn(B, H, H, N, device=dev).to(bf) if epi == L.EPI_MASK else None
     stats = torch.zeros(2 * N, dtype=torch.float64, device=dev) if epi == L.EPI_STATS else None
     d = L.ConvDesc(batch=B, height=H, width=H, ksize=k, src_channels=C, n_total=N, loader=loader, epilogue=epi,
-                   ktab=L.KTAB_GENERIC, tm=tm, n_block=nblk, src=src.data_ptr(), wpack=wp.data_ptr(), bias=bias.data_ptr(),
+                   ktab=ktab, tm=tm, n_block=nblk, src=src.data_ptr(), src2=src2.data_ptr() if src2 is not None else None,
+                   wpack=wp.data_ptr(), bias=bias.data_ptr(),
                    act=act.data_ptr() if act is not None else None, out=out.data_ptr(),
                    stats=stats.data_ptr() if stats is not None else None)
     s = L.stream_ptr()
