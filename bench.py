@@ -31,6 +31,9 @@ E0_FLOPS = 19_660_800             # encoder conv 0 needs no data-gradient
 CRITIC_CKPT = os.path.join(ROOT, "critic-vae_b200", "saved-networks",
                            "critic-rewidx=1-cepochs=15-datamode=trunk-datasize=99999-shift=12-chfak=1-dropout=0.3.pt")
 METRIC = "VAE train frames/s (fwd+bwd+loss+Adam)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the family's launches of one step) from the
+# ncu --set full capture summarised in profiles/r01_gemm_full_v2.md (batch 256)
+NCU_TRAFFIC = {"conv_gemm": 13.24e6, "conv_wgrad": 27.80e6}
 
 
 def peaks():
@@ -269,7 +272,8 @@ def run_b200(args):
     dominant = max(fam_ms, key=fam_ms.get)
     ach = flops[dominant] / (fam_ms[dominant] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": dominant, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC.get(dominant) if B == 256 else None, "traffic_unit": "bytes per launch (ncu, profiles/r01_gemm_full_v2.md)",
+                "peak_source": peak_src,
                 "launches_per_step": fam_calls[dominant], "ms_per_step_in_kernel": fam_ms[dominant],
                 "families": {k: {"ms_per_step": fam_ms[k], "launches": fam_calls[k],
                                  "achieved_tflops": flops[k] / (fam_ms[k] * 1e-3) / 1e12} for k in fam_ms}}
