@@ -357,8 +357,8 @@ __device__ __forceinline__ void mma_role_ks(const ConvArgs& a, PipeBars& bars, u
 // --------------------------------------------------------------------------------------------
 static constexpr int kPipeThreads = 320;
 static constexpr int kProducerThreads = 128;  // warps 6-9
-static size_t kStageBytesMax = getenv("CVAE_STAGE_KB") ? (size_t)atoi(getenv("CVAE_STAGE_KB")) * 1024 : 16 * 1024;
-static int kMaxGroupPlanes = getenv("CVAE_GROUP_PLANES") ? atoi(getenv("CVAE_GROUP_PLANES")) : 8;
+static size_t kStageBytesMax = getenv("CVAE_STAGE_KB") ? (size_t)atoi(getenv("CVAE_STAGE_KB")) * 1024 : 0;   // 0: automatic
+static int kMaxGroupPlanes = getenv("CVAE_GROUP_PLANES") ? atoi(getenv("CVAE_GROUP_PLANES")) : 0;         // 0: automatic
 static constexpr size_t kDynSmemMax = 216 * 1024;  // 227 KB per CTA minus static shared memory (barriers, statistics scratch)
 
 template <int LOADER, int EPI, int N, int KW>
@@ -753,41 +753,10 @@ static int conv_sequential(const cvae_conv_desc* d, ConvArgs& a, cudaStream_t st
     return CVAE_EINVAL;
 }
 
-extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    CVAE_REQUIRE(d != nullptr, CVAE_EINVAL, "conv_gemm: null descriptor");
-    CVAE_REQUIRE(d->ksize == 5 || d->ksize == 3, CVAE_EINVAL, "conv_gemm: ksize %d", d->ksize);
-    CVAE_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0, CVAE_EINVAL, "conv_gemm: empty shape");
-    CVAE_REQUIRE(d->n_total % 16 == 0 && d->n_total > 0, CVAE_EINVAL, "conv_gemm: n_total %d", d->n_total);
-    CVAE_REQUIRE(d->src && d->wpack && d->out, CVAE_EINVAL, "conv_gemm: null tensor");
-    if (d->ktab == CVAE_KTAB_PAIR8)
-        CVAE_REQUIRE(d->src_channels == 8 && d->ksize == 5, CVAE_EINVAL, "conv_gemm: PAIR8 needs 8 channels, 5x5");
-    else
-        CVAE_REQUIRE(d->src_channels % 16 == 0, CVAE_EINVAL, "conv_gemm: src_channels %d", d->src_channels);
-
-    ConvArgs a{};
-    a.B = d->batch; a.H = d->height; a.W = d->width; a.KW = d->ksize; a.pad = d->ksize / 2;
-    a.PW = a.W + a.pad; a.IH = a.H + a.pad;
-    a.dPW = make_fastdiv(a.PW); a.dIH = make_fastdiv(a.IH);
-    a.nb_pack = d->n_total < 128 ? d->n_total : 128;
-    CVAE_REQUIRE(d->n_total % a.nb_pack == 0, CVAE_EINVAL, "conv_gemm: n_total %d not a multiple of %d", d->n_total, a.nb_pack);
-    a.c_total = d->n_total;
-    a.ksteps = cvae_conv_ksteps(d->ksize, d->src_channels, d->ktab);
-    a.ktab_mode = d->ktab;
-    a.halo = a.pad * a.PW + a.pad;
-    a.wpack = (const __nv_bfloat16*)d->wpack; a.out = d->out;
-    a.bias = d->bias; a.act = (const __nv_bfloat16*)d->act; a.stats = d->stats;
-    a.fault = fault_flag();
-    a.dbg = g_dbg_counters;
-    a.dbg_flags = getenv("CVAE_DBG_FLAGS") ? atoi(getenv("CVAE_DBG_FLAGS")) : 0;
-    CVAE_REQUIRE(a.fault != nullptr, CVAE_ECUDA, "conv_gemm: fault flag unavailable");
-    const int all_planes = d->src_channels / 8;
-    a.ps = PlaneSrc{a.B, a.H, a.W, a.pad, a.PW, a.IH, all_planes,
-                    (d->loader == CVAE_LOAD_S2D) ? d->src_channels / 4 : d->src_channels, 0, d->src, d->src2};
-
-    if (getenv("CVAE_SEQ_FP32") && (d->loader == CVAE_LOAD_NCHW3 || d->loader == CVAE_LOAD_S2D_NCHW3_DTANH))
-        return conv_sequential(d, a, stream);
-
+// Tiling policy of the pipelined kernel for one (channel-group size, weight-stage size) choice; fails with
+// CVAE_EINVAL when the plane buffers and a useful weight ring do not fit shared memory.
+static int plan_pipe(const cvae_conv_desc* d, ConvArgs& a, int all_planes, int max_group_planes, size_t stage_cap, size_t* smem_out,
+                     int* n_out) {
     // ---- tiling policy of the pipelined kernel -----------------------------------------------------
     const long total_v = (long)a.B * a.IH * a.PW - (long)a.pad * a.PW;  // pixels from first to last valid row
     const int total_tiles = (int)((total_v + 127) / 128);
@@ -795,7 +764,7 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     // channel groups of <= 128 channels (16 planes)
     a.planes = all_planes;
     a.ncg = 1;
-    while (a.planes > kMaxGroupPlanes && a.planes % 4 == 0) { a.planes /= 2; a.ncg *= 2; }
+    while (a.planes > max_group_planes && a.planes % 4 == 0) { a.planes /= 2; a.ncg *= 2; }
     if (d->ktab == CVAE_KTAB_PAIR8) a.kpg = 13;
     else a.kpg = d->ksize * d->ksize * (a.planes / 2);
 
@@ -849,10 +818,10 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     CVAE_REQUIRE((G & (G - 1)) == 0, CVAE_EINVAL, "conv_gemm: channel pairs per group must be a power of two");
     a.rotate = getenv("CVAE_NO_ROTATE") ? 0 : 1;
     a.kgroup = (G % 4 == 0) ? 4 : (G % 2 == 0 ? 2 : 1);
-    while (a.kgroup > 1 && (size_t)a.kgroup * N * 32 > kStageBytesMax) a.kgroup /= 2;
+    while (a.kgroup > 1 && (size_t)a.kgroup * N * 32 > stage_cap) a.kgroup /= 2;
     a.ksps = a.kgroup;
     for (int c = a.kgroup; c <= run; c += a.kgroup)
-        if (run % c == 0 && a.kpg % c == 0 && (size_t)c * N * 32 <= kStageBytesMax) a.ksps = c;
+        if (run % c == 0 && a.kpg % c == 0 && (size_t)c * N * 32 <= stage_cap) a.ksps = c;
     if (pair8) a.ksps = a.kgroup = 13;   // one resident 13-step block
     const size_t stage_bytes = (size_t)a.ksps * N * 32;
     const long budget = (long)kDynSmemMax - 2 * (long)a.buf_bytes - (long)a.kpg * 8 - 64;
@@ -863,7 +832,64 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     a.resident = (a.n_blocks == 1 && stages_total <= nstages) ? 1 : 0;
     if (a.resident) nstages = stages_total;
     a.nstages = nstages;
-    const size_t smem = 2 * (size_t)a.buf_bytes + (size_t)nstages * stage_bytes + (size_t)a.kpg * 8 + 64;
+    *smem_out = 2 * (size_t)a.buf_bytes + (size_t)nstages * stage_bytes + (size_t)a.kpg * 8 + 64;
+    *n_out = N;
+    return CVAE_OK;
+
+}
+
+extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVAE_REQUIRE(d != nullptr, CVAE_EINVAL, "conv_gemm: null descriptor");
+    CVAE_REQUIRE(d->ksize == 5 || d->ksize == 3, CVAE_EINVAL, "conv_gemm: ksize %d", d->ksize);
+    CVAE_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0, CVAE_EINVAL, "conv_gemm: empty shape");
+    CVAE_REQUIRE(d->n_total % 16 == 0 && d->n_total > 0, CVAE_EINVAL, "conv_gemm: n_total %d", d->n_total);
+    CVAE_REQUIRE(d->src && d->wpack && d->out, CVAE_EINVAL, "conv_gemm: null tensor");
+    if (d->ktab == CVAE_KTAB_PAIR8)
+        CVAE_REQUIRE(d->src_channels == 8 && d->ksize == 5, CVAE_EINVAL, "conv_gemm: PAIR8 needs 8 channels, 5x5");
+    else
+        CVAE_REQUIRE(d->src_channels % 16 == 0, CVAE_EINVAL, "conv_gemm: src_channels %d", d->src_channels);
+
+    ConvArgs a{};
+    a.B = d->batch; a.H = d->height; a.W = d->width; a.KW = d->ksize; a.pad = d->ksize / 2;
+    a.PW = a.W + a.pad; a.IH = a.H + a.pad;
+    a.dPW = make_fastdiv(a.PW); a.dIH = make_fastdiv(a.IH);
+    a.nb_pack = d->n_total < 128 ? d->n_total : 128;
+    CVAE_REQUIRE(d->n_total % a.nb_pack == 0, CVAE_EINVAL, "conv_gemm: n_total %d not a multiple of %d", d->n_total, a.nb_pack);
+    a.c_total = d->n_total;
+    a.ksteps = cvae_conv_ksteps(d->ksize, d->src_channels, d->ktab);
+    a.ktab_mode = d->ktab;
+    a.halo = a.pad * a.PW + a.pad;
+    a.wpack = (const __nv_bfloat16*)d->wpack; a.out = d->out;
+    a.bias = d->bias; a.act = (const __nv_bfloat16*)d->act; a.stats = d->stats;
+    a.fault = fault_flag();
+    a.dbg = g_dbg_counters;
+    a.dbg_flags = getenv("CVAE_DBG_FLAGS") ? atoi(getenv("CVAE_DBG_FLAGS")) : 0;
+    CVAE_REQUIRE(a.fault != nullptr, CVAE_ECUDA, "conv_gemm: fault flag unavailable");
+    const int all_planes = d->src_channels / 8;
+    a.ps = PlaneSrc{a.B, a.H, a.W, a.pad, a.PW, a.IH, all_planes,
+                    (d->loader == CVAE_LOAD_S2D) ? d->src_channels / 4 : d->src_channels, 0, d->src, d->src2};
+
+    if (getenv("CVAE_SEQ_FP32") && (d->loader == CVAE_LOAD_NCHW3 || d->loader == CVAE_LOAD_S2D_NCHW3_DTANH))
+        return conv_sequential(d, a, stream);
+
+    // ---- tiling policy of the pipelined kernel: largest channel groups (fewest plane refills, longest contiguous
+    // weight runs) and weight stages that fit; tools/conv_bench.py sweeps showed 16-plane groups and 32 KB stages
+    // ahead wherever they fit (the MMA thread pays a fixed cost per stage) ------------------------------------
+    size_t smem = 0;
+    int N = 0;
+    {
+        const int gp_env = kMaxGroupPlanes, gps[2] = {gp_env > 0 ? gp_env : 16, 8};
+        const size_t caps[2] = {kStageBytesMax ? kStageBytesMax : 32 * 1024, 16 * 1024};
+        int rc = CVAE_EINVAL;
+        for (int gi = 0; gi < 2 && rc != CVAE_OK; ++gi)
+            for (int ci = 0; ci < 2 && rc != CVAE_OK; ++ci) {
+                ConvArgs trial = a;
+                rc = plan_pipe(d, trial, all_planes, gps[gi], caps[ci], &smem, &N);
+                if (rc == CVAE_OK) a = trial;
+            }
+        if (rc != CVAE_OK) return rc;
+    }
 
 #define CVAE_CASE(L_, E_, N_, K_) \
     if (d->loader == (L_) && d->epilogue == (E_) && N == (N_) && d->ksize == (K_)) return launch_pipe<L_, E_, N_, K_>(a, smem, stream);

@@ -621,6 +621,15 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
     else rc = launch_wgrad<CVAE_LOAD_S2D_NCHW3_DTANH, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     if (rc != CVAE_OK) return rc;
 
+    if (d->fold_stream != nullptr && d->fold_stream != stream_) {   // fold on a second stream, ordered after the GEMM
+        cudaEvent_t ev;
+        CVAE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e1 = cudaEventRecord(ev, stream);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent((cudaStream_t)d->fold_stream, ev, 0) : e1;
+        cudaEventDestroy(ev);   // released once the recorded work has completed
+        CVAE_REQUIRE(e2 == cudaSuccess, CVAE_ECUDA, "conv_wgrad: fold stream dependency failed: %s", cudaGetErrorString(e2));
+        stream = (cudaStream_t)d->fold_stream;
+    }
     f.dbg_linear = getenv("CVAE_FOLD_LINEAR") ? 1 : 0;
     f.kind = d->kind; f.cout = d->cout; f.cin = d->cin; f.splits = splits; f.split_floats = a.split_floats;
     f.m_total = a.m_total; f.n = n; f.partial = a.partial; f.dw = (float*)d->dw; f.dbias = (float*)d->dbias;

@@ -39,7 +39,7 @@ class WgradDesc(ctypes.Structure):
                 ("width", ctypes.c_int32), ("cout", ctypes.c_int32), ("cin", ctypes.c_int32),
                 ("splits", ctypes.c_int32),
                 ("x", c_void_p), ("dy", c_void_p), ("dy2", c_void_p), ("dw", c_void_p),
-                ("dbias", c_void_p), ("workspace", c_void_p)]
+                ("dbias", c_void_p), ("workspace", c_void_p), ("fold_stream", c_void_p)]
 
 
 lib.cvae_last_error.restype = ctypes.c_char_p

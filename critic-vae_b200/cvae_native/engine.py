@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import torch
 
@@ -44,6 +45,9 @@ def msssim_window():
     k = torch.tensor([math.exp((i - 11 // 2) ** 2 / (2 * 1.5 ** 2)) for i in range(11)])
     k = k / k.sum()
     return (ctypes.c_float * 11)(*[float(v) for v in k])
+
+
+_SKIP_WGRAD = os.environ.get("CVAE_SKIP_WGRAD") is not None
 
 
 def _ptr(t):
@@ -113,6 +117,7 @@ class VAEEngine:
         # Weight gradients are leaves of the backward pass: with a side stream they run concurrently with the
         # data-gradient chain (fork / join with events, so the pair is CUDA-graph capturable).
         self.side_stream = None
+        self.fold_stream = None     # third stream: split-K folds beside the next weight-gradient GEMM
 
     # ---- parameters ---------------------------------------------------------------------------
     def view(self, name, buf=None):
@@ -263,13 +268,19 @@ class VAEEngine:
 
     # ---- backward -----------------------------------------------------------------------------
     def _wgrad(self, g, name, **kw):
+        if _SKIP_WGRAD:     # timing experiment only (CVAE_SKIP_WGRAD=1): how long is the step without weight gradients?
+            return
         d = L.WgradDesc(**{k: (_ptr(v) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
         need = int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d)))
-        if self._wgrad_ws is None or self._wgrad_ws.numel() < need:
-            self._wgrad_ws = torch.empty(max(need, 64 << 20), dtype=torch.uint8, device=self.device)
+        # one split-K workspace per layer: the fold of one layer overlaps the GEMM of the next
+        ws = self._wgrad_ws.get(name) if isinstance(self._wgrad_ws, dict) else None
+        if ws is None or ws.numel() < need:
+            if not isinstance(self._wgrad_ws, dict):
+                self._wgrad_ws = {}
+            ws = self._wgrad_ws[name] = torch.empty(need, dtype=torch.uint8, device=self.device)
         # A conv bias in front of BatchNorm has an exactly-zero gradient (the batch mean removes it): leave
         # the zero-initialised slot of the flat buffer untouched instead of writing rounding noise.
-        d.dw, d.workspace = _ptr(self.view(name + ".weight", g)), _ptr(self._wgrad_ws)
+        d.dw, d.workspace = _ptr(self.view(name + ".weight", g)), _ptr(ws)
         d.dbias = None if name.startswith("encoder.") else _ptr(self.view(name + ".bias", g))
         if self.side_stream is None or self.profile is not None:
             self._timed("conv_wgrad", lambda: L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr())))
@@ -277,6 +288,9 @@ class VAEEngine:
         ev = torch.cuda.Event()
         ev.record()
         self.side_stream.wait_event(ev)
+        if self.fold_stream is not None:
+            d.fold_stream = self.fold_stream.cuda_stream
+            self._fold_used = True
         with torch.cuda.stream(self.side_stream):
             L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()))
         self._side_used = True
@@ -299,7 +313,7 @@ class VAEEngine:
         g = self.gflat if g is None else g
         B, s = ws.B, L.stream_ptr()
         G = lambda n: self.view(n, g)
-        self._side_used = False
+        self._side_used = self._fold_used = False
         if self._bwd_packed is not None:
             torch.cuda.current_stream().wait_event(self._bwd_packed)
             self._bwd_packed = None
@@ -345,6 +359,8 @@ class VAEEngine:
                            epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
         if self._side_used:
             torch.cuda.current_stream().wait_stream(self.side_stream)
+        if self._fold_used:
+            torch.cuda.current_stream().wait_stream(self.fold_stream)
         return g
 
     # ---- optimizer ----------------------------------------------------------------------------

@@ -40,6 +40,7 @@ class TrainStep:
         self._graphs = None
         if os.environ.get("CVAE_NO_SIDE_STREAM") is None:
             self.eng.side_stream = torch.cuda.Stream()
+            self.eng.fold_stream = torch.cuda.Stream()
         self._use_graph = use_graph
         self.launches_per_step = None
 

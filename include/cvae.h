@@ -100,6 +100,8 @@ typedef struct {
     void* dw;                    /* fp32 [cout][cin][5][5], overwritten */
     void* dbias;                 /* fp32 [cout], overwritten (may be NULL) */
     void* workspace;             /* >= cvae_conv_wgrad_workspace_bytes(d) */
+    void* fold_stream;           /* optional second stream for the partial-sum fold (NULL: same stream); the fold is
+                                    ordered after the GEMM with an event, the caller joins fold_stream itself */
 } cvae_wgrad_desc;
 
 int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d);
