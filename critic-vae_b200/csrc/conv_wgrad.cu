@@ -13,6 +13,8 @@
 // 3x3 phase taps of the up-sample-folded decoder convs back onto the 5x5 filter).
 //
 // Replaces autograd's weight/bias gradients of nn.Conv2d at vae_nets.py:69,74,79,84,117-133.
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "planes.cuh"
@@ -423,6 +425,348 @@ static int launch_wgrad(const WgradArgs& a, size_t smem, dim3 grid, cudaStream_t
     return CVAE_OK;
 }
 
+
+// =============================================================================================
+// TMA-fed variant for layers whose operands have >= 64 channels on both sides (E2, E3, D0, D1).
+//
+// Operand tiles are MN-major with 128-byte rows ([pixel][64 channels], SWIZZLE_128B), written by
+// cp.async.bulk.tensor boxes {64 ch, W + pad, rows, images} of the NHWC tensors: the zero padding columns / rows of
+// the virtual pixel space come from out-of-bounds fill, so a box lands as consecutive virtual pixels.  A filter tap is
+// the B descriptor's start address moved by dy * PW + dx rows; tools/umma_probe_swz.py verified that tcgen05.mma
+// applies the 128-byte swizzle to ABSOLUTE shared-memory address bits (base offset 0), so a tile written by TMA can be
+// read from any 128-byte row.  tools/tma_probe.cu: such boxes arrive at ~80 B/clk/SM against ~15 B/clk for the
+// 16-byte-granular planes.
+// Chunk = NB whole images (small maps) or R rows of one image; everything TMA never writes (margins around the B box,
+// the K tail that rounds a chunk up to 16 pixels) is zeroed once at kernel start and stays zero.
+// =============================================================================================
+struct WgTmaArgs {
+    int rows_mode;              // 0: chunk = NB whole images, 1: chunk = RA rows of one image
+    int NB, RA, pad;            // images per box; rows per A box (B box has RA + 2 pad rows in rows mode)
+    int blocks_per_image;       // rows mode: row blocks per image
+    int num_chunks, splits;
+    int kc;                     // K per chunk (multiple of 16)
+    int b_blocks;               // 64-channel column blocks of B (N / 64)
+    int a_block_bytes, b_block_bytes;   // column-block strides (multiples of 1024)
+    int b_box_row;              // 128-byte row inside a B block where the box lands
+    int b_base_row;             // B row that pairs with A row 0 for the centre tap
+    int buf_bytes, a_region, nbuf;   // nbuf: 2..4 chunk buffers (TMA latency is longer than the MMAs of a short chunk)
+    uint32_t tx_bytes;          // bytes of all boxes of one chunk
+    int phase_maps;             // A column block q of M block mb: 1 -> tensor map mb*2+q (channel 0), 0 -> map 0, channel (mb*2+q)*64
+    int ones_off, ones_stride;  // bias pseudo-group operand: no-swizzle plane pair of ones after the buffers (0: none)
+    int m_rows, groups_total, gpc, split_floats;
+    int tap_row[kMaxGroups];    // dy * PW + dx per group
+    int gn[kMaxGroups];         // UMMA N per group
+    int gout[kMaxGroups];       // float offset of the group's block in one split's partial
+    float* partial;
+    int* fault;
+};
+
+static constexpr int kWtThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kWtThreads, 1)
+conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                      const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                      const __grid_constant__ CUtensorMap mapB) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_full[4], bar_empty[4], bar_acc;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x, gset = blockIdx.y, mb = blockIdx.z;
+    const int g0 = gset * a.gpc, g1 = min(g0 + a.gpc, a.groups_total);
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        mbar_init(&bar_acc, 1);
+        mbar_fence_init();
+    }
+    int cols = 0;
+    for (int g = g0; g < g1; ++g) cols += a.gn[g];
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)cols) ncols <<= 1;
+    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+    // zero everything once (margins and K tails stay zero), then the ones tile
+    const int total16 = (a.nbuf * a.buf_bytes) >> 4;
+    for (int i = tid; i < total16; i += kWtThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (a.ones_off) {
+        for (int q = 0; q < 2; ++q) fill_ones_plane(smem + a.ones_off + (size_t)q * a.ones_stride, a.kc, tid, kWtThreads);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const int my_chunks = (a.num_chunks - split + a.splits - 1) / a.splits;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer --------------------------------------------
+        if (elect_one()) {
+            const CUtensorMap* mapsA[4] = {&mapA0, &mapA1, &mapA2, &mapA3};
+            bool alive = true;
+            for (int i = 0; i < my_chunks && alive; ++i) {
+                const int buf = i % a.nbuf;
+                const int chunk = split + i * a.splits;
+                alive = mbar_wait(&bar_empty[buf], ((i / a.nbuf) & 1) ^ 1, a.fault);
+                int n, ha, hb;
+                if (a.rows_mode) {
+                    n = chunk / a.blocks_per_image;
+                    ha = (chunk - n * a.blocks_per_image) * a.RA;
+                    hb = ha - a.pad;
+                } else {
+                    n = chunk * a.NB;
+                    ha = hb = -a.pad;
+                }
+                mbar_expect_tx(&bar_full[buf], a.tx_bytes);
+                const uint32_t A = smem_base + (uint32_t)buf * a.buf_bytes;
+                const uint32_t Bp = A + a.a_region + (uint32_t)a.b_box_row * 128u;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int blk = mb * 2 + q;
+                    tma_load_4d(A + (uint32_t)q * a.a_block_bytes, a.phase_maps ? mapsA[blk] : mapsA[0], a.phase_maps ? 0 : blk * 64, 0, ha, n,
+                                &bar_full[buf]);
+                }
+                for (int q = 0; q < a.b_blocks; ++q)
+                    tma_load_4d(Bp + (uint32_t)q * a.b_block_bytes, &mapB, q * 64, 0, hb, n, &bar_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ----------------------------------------------
+        if (elect_one()) {
+            bool alive = true;
+            // swizzled MN-major descriptors: LBO = column-block stride, SBO = 1024 (8 rows), layout type 2; the K loop
+            // moves both start addresses by 16 rows = 2048 B = 128 descriptor units
+            const uint32_t hi_sw = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lbo = (((uint32_t)a.a_block_bytes >> 4) & 0x3FFFu) << 16;
+            const uint32_t b_lbo = (((uint32_t)a.b_block_bytes >> 4) & 0x3FFFu) << 16;
+            const uint32_t hi_ones = (((uint32_t)a.ones_stride >> 4) & 0x3FFFu) | (1u << 14);   // no swizzle: SBO = plane stride
+            const uint32_t ones_lbo = (128u >> 4) << 16;
+            const int ksteps = a.kc >> 4;
+            for (int i = 0; i < my_chunks && alive; ++i) {
+                const int buf = i % a.nbuf;
+                alive = mbar_wait(&bar_full[buf], (i / a.nbuf) & 1, a.fault);
+                tc_fence_after();
+                const uint32_t A16 = (((smem_base + (uint32_t)buf * a.buf_bytes) & 0x3FFFFu) >> 4);
+                const uint32_t B16 = A16 + ((uint32_t)a.a_region >> 4);
+                uint32_t col = tmem_base;
+                for (int g = g0; g < g1; ++g) {
+                    const int n = a.gn[g];
+                    const uint32_t idesc = umma_idesc_bf16(n, kMajorMN, kMajorMN);
+                    uint32_t a_lo = A16 | a_lbo;
+                    uint32_t b_lo, b_hi, b_step;
+                    if (n == 16) {   // bias pseudo-group against the ones tile
+                        b_lo = (((smem_base + (uint32_t)a.ones_off) & 0x3FFFFu) >> 4) | ones_lbo;
+                        b_hi = hi_ones;
+                        b_step = 16u;    // 16 pixel slots of 16 B
+                    } else {
+                        b_lo = (B16 + (uint32_t)(a.b_base_row + a.tap_row[g]) * 8u) | b_lbo;
+                        b_hi = hi_sw;
+                        b_step = 128u;
+                    }
+                    uint32_t acc = i > 0 ? 1u : 0u;
+                    int k = 0;
+                    for (; k + 4 <= ksteps; k += 4) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            umma_bf16(col, ((uint64_t)hi_sw << 32) | (uint64_t)(a_lo + (uint32_t)(j * 128)),
+                                      ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)j * b_step), idesc, j == 0 ? acc : 1u);
+                        acc = 1u;
+                        a_lo += 4u * 128u;
+                        b_lo += 4u * b_step;
+                    }
+                    for (; k < ksteps; ++k) {
+                        umma_bf16(col, ((uint64_t)hi_sw << 32) | (uint64_t)a_lo, ((uint64_t)b_hi << 32) | (uint64_t)b_lo, idesc, acc);
+                        acc = 1u;
+                        a_lo += 128u;
+                        b_lo += b_step;
+                    }
+                    col += (uint32_t)n;
+                }
+                umma_commit(&bar_empty[buf]);
+            }
+            umma_commit(&bar_acc);
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------ epilogue (8 warps: lane quarter = warp % 4, groups dealt by parity) -------------
+        mbar_wait(&bar_acc, 0, a.fault);
+        tc_fence_after();
+        const int quarter = warp & 3, par = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        float* base = a.partial + (size_t)split * a.split_floats;
+        uint32_t col = 0;
+        for (int g = g0; g < g1; ++g) {
+            const int n = a.gn[g];
+            if (((g - g0) & 1) != par) { col += n; continue; }
+            float* o = base + a.gout[g] + ((size_t)mb * a.m_rows + row) * n;
+            for (int c = 0; c < n; c += 16) {
+                uint32_t raw[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + col + c, raw);
+                tmem_wait_ld();
+                if (row < a.m_rows) {
+                    float4* o4 = reinterpret_cast<float4*>(o + c);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        o4[q] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
+                                            __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+                }
+            }
+            col += n;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem_base, ncols);
+}
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (TensorMapEncodeFn)p;
+    }
+    return fn;
+}
+
+// bf16 tensor viewed as {channels, w, h, n} with element strides (in elements) for w, h, n; box {64, bw, bh, bn}, SWIZZLE_128B
+static bool encode_map(CUtensorMap* m, const void* base, int channels, int W, int H, int B, long sw, long sh, long sn, int bw, int bh, int bn) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t gdim[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Plans and launches the TMA variant; returns 1 when the shape is not eligible (the caller falls back to the plane kernel).
+static int launch_wgrad_tma(const cvae_wgrad_desc* d, const WgradArgs& base, int n, int gsets, int H, int W, int pad, cudaStream_t stream,
+                            int* splits_out) {
+    const int mtot = (d->kind == CVAE_WGRAD_5X5) ? d->cout : 4 * d->cout;
+    if (getenv("CVAE_WG_NO_TMA")) return 1;
+    if (!(d->kind == CVAE_WGRAD_5X5 || d->kind == CVAE_WGRAD_PHASE)) return 1;
+    if (mtot % 128 != 0 || d->cin % 64 != 0 || d->cin > 256) return 1;
+    if (d->kind == CVAE_WGRAD_PHASE && d->cout != 64) return 1;
+    if (d->kind == CVAE_WGRAD_5X5 && d->cout % 64 != 0) return 1;
+    if (!tensor_map_encoder()) return 1;
+    const int PW = W + pad, IH = H + pad, halo = pad * PW + pad;
+    WgTmaArgs t{};
+    t.pad = pad;
+    t.b_blocks = d->cin / 64;
+    const bool bias = d->dbias != nullptr;
+    const int m_blocks = mtot / 128;
+    int splits = sm_count() / (gsets * m_blocks);
+    if (splits < 1) splits = 1;
+    const size_t cap = 212 * 1024;
+    auto plan = [&](int rows_mode, int NB, int RA) -> bool {
+        const int kreal = rows_mode ? RA * PW : NB * IH * PW;
+        const int kc = (kreal + 15) / 16 * 16;
+        const int box_rows_b = rows_mode ? (RA + 2 * pad) * PW : kreal;
+        const int b_box_row = rows_mode ? 8 : (halo + 7) / 8 * 8;
+        const int b_rows = b_box_row + box_rows_b + (kc - kreal) + halo + 8;
+        const int a_block = (kc * 128 + 1023) & ~1023, b_block = (b_rows * 128 + 1023) & ~1023;
+        const size_t buf = (size_t)2 * a_block + (size_t)t.b_blocks * b_block;
+        const size_t ones = bias ? (size_t)2 * (((kc * 16) + 127) & ~127) : 0;
+        if (2 * buf + ones > cap || a_block >= (1 << 18) || b_block >= (1 << 18)) return false;
+        int nbuf = (int)((cap - ones) / buf);
+        t.nbuf = nbuf > 4 ? 4 : nbuf;
+        t.rows_mode = rows_mode; t.NB = NB; t.RA = RA; t.kc = kc;
+        t.b_box_row = b_box_row;
+        t.b_base_row = b_box_row + (rows_mode ? pad * PW : 0);
+        t.a_block_bytes = a_block; t.b_block_bytes = b_block;
+        t.a_region = 2 * a_block;
+        t.buf_bytes = (int)buf;
+        t.ones_off = bias ? (int)(t.nbuf * buf) : 0;
+        t.ones_stride = (kc * 16 + 127) & ~127;
+        t.tx_bytes = (uint32_t)(2 * kreal * 128 + t.b_blocks * box_rows_b * 128);
+        t.blocks_per_image = rows_mode ? (H + RA - 1) / RA : 1;
+        t.num_chunks = rows_mode ? d->batch * t.blocks_per_image : (d->batch + NB - 1) / NB;
+        return true;
+    };
+    // Candidates: NB whole images per chunk (pad rows included) or RA rows of one image.  Pick the one that spends the
+    // fewest K steps per image among those with a useful chunk length (>= 96 pixels) and >= 2 chunks per CTA.
+    bool ok = false;
+    {
+        const int per_cta_images = (d->batch + splits - 1) / splits;
+        int best_mode = -1, best_nb = 0, best_ra = 0;
+        double best_cost = 1e30;
+        auto consider = [&](int rows_mode, int NB, int RA) {
+            if (!plan(rows_mode, NB, RA)) return;
+            const double k_per_image = rows_mode ? (double)t.blocks_per_image * t.kc : (double)t.kc / NB;
+            const double chunks_per_cta = (double)t.num_chunks / splits;
+            double cost = k_per_image;
+            if (t.kc < 96) cost *= 96.0 / t.kc;            // per-chunk overhead of short chunks
+            if (chunks_per_cta < 2.0) cost *= 2.0;         // no load / MMA overlap
+            if (t.nbuf < 3) cost *= 1.15;                  // two buffers do not hide the TMA latency of short chunks
+            if (cost < best_cost) { best_cost = cost; best_mode = rows_mode; best_nb = NB; best_ra = RA; }
+        };
+        for (int NB = 1; NB <= 256 && NB <= per_cta_images && IH <= 256; ++NB) consider(0, NB, IH);
+        for (int RA = 1; RA <= H; ++RA) consider(1, 1, RA);
+        if (best_mode >= 0) ok = plan(best_mode, best_nb, best_ra);
+    }
+    if (!ok) return 1;
+    if (splits > t.num_chunks) splits = t.num_chunks;
+    t.splits = splits;
+
+    // tensor maps
+    CUtensorMap mA[4], mB;
+    const int ba_rows = t.rows_mode ? t.RA : IH, bb_rows = t.rows_mode ? t.RA + 2 * pad : IH;
+    bool enc_ok = true;
+    if (d->kind == CVAE_WGRAD_5X5) {
+        enc_ok = encode_map(&mA[0], d->dy, d->cout, W, H, d->batch, d->cout, (long)W * d->cout, (long)H * W * d->cout, PW, ba_rows, t.NB);
+        mA[1] = mA[2] = mA[3] = mA[0];
+        t.phase_maps = 0;
+    } else {   // dY at [B][2H][2W][cout]: one strided view per output phase (a, b)
+        const long c = d->cout;
+        for (int ab = 0; ab < 4 && enc_ok; ++ab) {
+            const __nv_bfloat16* b0 = (const __nv_bfloat16*)d->dy + ((long)(ab >> 1) * 2 * W + (ab & 1)) * c;
+            enc_ok = encode_map(&mA[ab], b0, d->cout, W, H, d->batch, 2 * c, 2L * 2 * W * c, 4L * H * W * c, PW, ba_rows, t.NB);
+        }
+        t.phase_maps = 1;
+    }
+    enc_ok = enc_ok && encode_map(&mB, d->x, d->cin, W, H, d->batch, d->cin, (long)W * d->cin, (long)H * W * d->cin, PW, bb_rows, t.NB);
+    if (!enc_ok) return 1;
+
+    t.m_rows = 128;
+    t.groups_total = base.groups_total; t.gpc = base.gpc; t.split_floats = base.split_floats;
+    for (int g = 0; g < base.groups_total; ++g) {
+        t.gn[g] = base.g[g].n;
+        t.gout[g] = base.g[g].out_off;
+        t.tap_row[g] = base.g[g].n == 16 ? 0 : base.g[g].b_off / 16 - halo;
+    }
+    t.partial = base.partial; t.fault = base.fault;
+    const size_t smem = (size_t)t.nbuf * t.buf_bytes + (t.ones_off ? (size_t)2 * t.ones_stride : 0);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        CVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    if (getenv("CVAE_DEBUG"))
+        fprintf(stderr, "conv_wgrad_tma kind %d %dx%d cout=%d cin=%d: %s NB=%d RA=%d kc=%d nbuf=%d chunks=%d splits=%d gsets=%d mblocks=%d buf=%d smem=%zu\n",
+                d->kind, H, W, d->cout, d->cin, t.rows_mode ? "rows" : "images", t.NB, t.RA, t.kc, t.nbuf, t.num_chunks, splits, gsets, m_blocks,
+                t.buf_bytes, smem);
+    dim3 grid(splits, gsets, m_blocks);
+    conv_wgrad_tma_kernel<<<grid, kWtThreads, smem, stream>>>(t, mA[0], mA[1], mA[2], mA[3], mB);
+    CVAE_LAUNCH_CHECK();
+    *splits_out = splits;
+    return CVAE_OK;
+}
+
 }  // namespace cvae
 
 using namespace cvae;
@@ -614,8 +958,10 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
         fprintf(stderr, "conv_wgrad kind %d B=%d %dx%d cout=%d cin=%d: n=%d groups=%d gpc=%d gsets=%d mblocks=%d splits=%d kc=%d chunks=%d "
                         "buf=%d B smem=%zu\n", d->kind, d->batch, H, W, d->cout, d->cin, n, a.groups_total, a.gpc, gsets, a.m_blocks, splits,
                 a.kc, a.num_chunks, a.buf_bytes, (size_t)2 * a.buf_bytes);
-    int rc;
-    if (la == CVAE_LOAD_NHWC) rc = launch_wgrad<CVAE_LOAD_NHWC, CVAE_LOAD_NHWC>(a, smem, grid, stream);
+    int rc = launch_wgrad_tma(d, a, n, gsets, H, W, pad, stream, &splits);
+    if (rc < 0) return rc;
+    if (rc == CVAE_OK) { /* TMA variant launched (splits may differ) */ }
+    else if (la == CVAE_LOAD_NHWC) rc = launch_wgrad<CVAE_LOAD_NHWC, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     else if (la == CVAE_LOAD_S2D) rc = launch_wgrad<CVAE_LOAD_S2D, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     else if (la == CVAE_LOAD_NCHW3) rc = launch_wgrad<CVAE_LOAD_NCHW3, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     else rc = launch_wgrad<CVAE_LOAD_S2D_NCHW3_DTANH, CVAE_LOAD_NHWC>(a, smem, grid, stream);

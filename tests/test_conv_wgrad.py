@@ -31,7 +31,9 @@ def _check(dw, db, ref_w, ref_b):
 
 
 @pytest.mark.parametrize("B,Cin,Cout,HW,splits", [(3, 32, 64, 32, 0), (4, 64, 128, 16, 0), (5, 128, 256, 8, 0),
-                                                 (6, 256, 128, 4, 0), (3, 32, 64, 32, 1), (7, 64, 128, 16, 3)])
+                                                 (6, 256, 128, 4, 0), (3, 32, 64, 32, 1), (7, 64, 128, 16, 3),
+                                                 # TMA-fed variant: several chunks per CTA, image boxes running past the batch
+                                                 (41, 128, 256, 8, 0), (33, 64, 128, 16, 0), (50, 256, 128, 4, 0)])
 def test_wgrad_5x5(B, Cin, Cout, HW, splits):
     L = _native()
     x, dy = rb(_rand((B, Cin, HW, HW), 31)), rb(_rand((B, Cout, HW, HW), 32))
@@ -40,7 +42,7 @@ def test_wgrad_5x5(B, Cin, Cout, HW, splits):
     _check(dw, db, ref_w, dy.double().sum((0, 2, 3)).float())
 
 
-@pytest.mark.parametrize("B,Cin,Cout,HW", [(3, 128, 64, 4), (3, 64, 32, 8), (2, 32, 32, 16)])
+@pytest.mark.parametrize("B,Cin,Cout,HW", [(3, 128, 64, 4), (3, 64, 32, 8), (2, 32, 32, 16), (45, 128, 64, 4)])
 def test_wgrad_upsample_folded(B, Cin, Cout, HW):
     L = _native()
     x, dy = rb(_rand((B, Cin, HW, HW), 33)), rb(_rand((B, Cout, 2 * HW, 2 * HW), 34))

@@ -27,7 +27,7 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
 }
 
 struct Args {
-    int planes, box_bytes, iters, images, nb, ih, pad, verify;
+    int planes, box_bytes, iters, images, nb, ih, pad, verify, inner;
     unsigned long long* cycles;
     uint4* dump;
 };
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ C
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
-    const int stride = (a.box_bytes + 127) & ~127;
+    const int stride = (a.box_bytes + 1023) & ~1023;
     if (warp == 0) {
         long long t0 = clock64();
         for (int it = 0; it < a.iters; ++it) {
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ C
             if (lane == 0) mbar_expect_tx(&bar[buf], (uint32_t)(a.planes * a.box_bytes));
             __syncwarp();
             for (int q = lane; q < a.planes; q += 32)
-                tma_load_4d(smem + (size_t)buf * a.planes * stride + (size_t)q * stride, &map, q * 8, 0, -a.pad, n0, &bar[buf]);
+                tma_load_4d(smem + (size_t)buf * a.planes * stride + (size_t)q * stride, &map, q * a.inner, 0, -a.pad, n0, &bar[buf]);
         }
         for (int it = (a.iters >= 2 ? a.iters - 2 : 0); it < a.iters; ++it) mbar_wait(&bar[it & 1], (it >> 1) & 1, &g_fault);
         long long t1 = clock64();
@@ -71,6 +71,7 @@ int main() {
         return 1;
     }
     struct Cfg { int H, C, R, NB, planes; };   // R rows per box (IH = whole image), NB images per box
+    const int inner = (getenv("TMA_INNER") ? atoi(getenv("TMA_INNER")) : 8);   // channels per box row: 8 (16 B, no swizzle) or 64 (128 B, SWIZZLE_128B)
     const Cfg cfgs[] = {{8, 128, 10, 5, 16}, {8, 128, 10, 5, 32}, {4, 256, 6, 16, 32}, {16, 64, 18, 2, 8}, {32, 32, 17, 1, 4}, {32, 64, 17, 1, 8},
                         {64, 32, 12, 1, 4}};
     const int B = 256, pad = 2;
@@ -85,14 +86,16 @@ int main() {
         CUtensorMap map;
         cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-        cuuint32_t box[4] = {8, (cuuint32_t)PW, (cuuint32_t)c.R, (cuuint32_t)c.NB};
+        cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)PW, (cuuint32_t)c.R, (cuuint32_t)c.NB};
+        if (inner > C) { printf("skip C=%d\n", C); cudaFree(d); continue; }
+        const int planes = inner == 8 ? c.planes : (C / inner);
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
         Args a{};
-        a.planes = c.planes; a.box_bytes = 16 * PW * c.R * c.NB; a.iters = 40; a.images = B; a.nb = c.NB; a.ih = c.R; a.pad = pad; a.verify = 1;
-        const int stride = (a.box_bytes + 127) & ~127;
+        a.planes = planes; a.box_bytes = 2 * inner * PW * c.R * c.NB; a.inner = inner; a.iters = 40; a.images = B; a.nb = c.NB; a.ih = c.R; a.pad = pad; a.verify = 1;
+        const int stride = (a.box_bytes + 1023) & ~1023;
         const size_t smem = (size_t)2 * a.planes * stride;
         if (smem > 220 * 1024) { printf("cfg too big\n"); continue; }
         cudaMalloc(&a.cycles, 148 * 8);
@@ -115,6 +118,20 @@ int main() {
         cudaMemcpy(dump.data(), a.dump, (size_t)a.planes * stride, cudaMemcpyDeviceToHost);
         const int it = a.iters - 1, n0 = ((0 * a.iters + it) * a.nb) % (B - a.nb + 1);
         long bad = 0;
+        if (inner == 64) {   // swizzled check: row = slot, 16-byte chunk ch of the 128-byte row sits at chunk (ch ^ (row & 7)) (absolute: planes are 1024 B aligned)
+            for (int q = 0; q < a.planes; ++q)
+                for (int slot = 0; slot < c.NB * c.R * PW; ++slot)
+                    for (int ch = 0; ch < 64; ++ch) {
+                        const int img = slot / (c.R * PW), rr = (slot / PW) % c.R, col = slot % PW, hh = rr - pad, n = n0 + img;
+                        uint16_t want = 0;
+                        if (hh >= 0 && hh < H && col < W) {
+                            __nv_bfloat16 v = h[(((size_t)n * H + hh) * W + col) * C + q * 64 + ch];
+                            want = *reinterpret_cast<uint16_t*>(&v);
+                        }
+                        const size_t byte = (size_t)q * stride + (size_t)slot * 128 + (size_t)(((ch >> 3) ^ (slot & 7)) << 4) + (ch & 7) * 2;
+                        if (dump[byte / 2] != want) ++bad;
+                    }
+        } else
         for (int q = 0; q < a.planes; ++q)
             for (int img = 0; img < c.NB; ++img)
                 for (int rr = 0; rr < c.R; ++rr)
@@ -126,7 +143,9 @@ int main() {
                                 __nv_bfloat16 v = h[(((size_t)n * H + hh) * W + col) * C + q * 8 + e];
                                 want = *reinterpret_cast<uint16_t*>(&v);
                             }
-                            const uint16_t got = dump[((size_t)q * stride + ((size_t)(img * c.R + rr) * PW + col) * 16) / 2 + e];
+                            uint16_t got;
+                            if (inner == 8) got = dump[((size_t)q * stride + ((size_t)(img * c.R + rr) * PW + col) * 16) / 2 + e];
+                            else got = 0;
                             if (got != want) ++bad;
                         }
         printf("   verify: %ld mismatches\n", bad);

@@ -21,6 +21,8 @@ struct ProbeArgs {
     uint32_t n;
     uint32_t use_bulk;            // copy the B image with cp.async.bulk instead of st.shared
     float* out;                   // [128][n]
+    uint32_t a_swz, b_swz;        // descriptor layout type (bits 61-63): 0 none, 2 = 128 B swizzle, 4 = 64 B, 6 = 32 B
+    uint32_t a_boff, b_boff;      // descriptor base offset (bits 49-51)
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
@@ -67,6 +69,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
             for (uint32_t k = 0; k < p.ksteps; ++k) {
                 uint64_t da = smem_desc(smem_u32(sa) + p.a_off + k * p.a_kstep, p.a_lbo, p.a_sbo);
                 uint64_t db = smem_desc(smem_u32(sb) + p.b_off + k * p.b_kstep, p.b_lbo, p.b_sbo);
+                da |= ((uint64_t)(p.a_swz & 7u) << 61) | ((uint64_t)(p.a_boff & 7u) << 49);
+                db |= ((uint64_t)(p.b_swz & 7u) << 61) | ((uint64_t)(p.b_boff & 7u) << 49);
                 umma_bf16(tmem_base, da, db, p.idesc, k > 0);
             }
         }
@@ -89,12 +93,27 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
     if (warp == 0) tmem_free(tmem_base, ncols);
 }
 
+extern "C" int probe_run_swz(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes,
+                             uint32_t a_off, uint32_t b_off, uint32_t a_lbo, uint32_t a_sbo,
+                             uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep, uint32_t b_kstep,
+                             uint32_t ksteps, uint32_t idesc, uint32_t n, uint32_t use_bulk, float* out,
+                             uint32_t a_swz, uint32_t b_swz, uint32_t a_boff, uint32_t b_boff);
+
 extern "C" int probe_run(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes,
                          uint32_t a_off, uint32_t b_off, uint32_t a_lbo, uint32_t a_sbo,
                          uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep, uint32_t b_kstep,
                          uint32_t ksteps, uint32_t idesc, uint32_t n, uint32_t use_bulk, float* out) {
+    return probe_run_swz(a_img, a_bytes, b_img, b_bytes, a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep, ksteps, idesc, n,
+                         use_bulk, out, 0, 0, 0, 0);
+}
+
+extern "C" int probe_run_swz(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes,
+                             uint32_t a_off, uint32_t b_off, uint32_t a_lbo, uint32_t a_sbo,
+                             uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep, uint32_t b_kstep,
+                             uint32_t ksteps, uint32_t idesc, uint32_t n, uint32_t use_bulk, float* out,
+                             uint32_t a_swz, uint32_t b_swz, uint32_t a_boff, uint32_t b_boff) {
     ProbeArgs p{(const uint8_t*)a_img, (const uint8_t*)b_img, a_bytes, b_bytes, a_off, b_off,
-                a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep, ksteps, idesc, n, use_bulk, out};
+                a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep, ksteps, idesc, n, use_bulk, out, a_swz, b_swz, a_boff, b_boff};
     size_t smem = ((a_bytes + 1023u) & ~1023u) + ((b_bytes + 1023u) & ~1023u) + 1024;
     cudaError_t e = cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
