@@ -97,9 +97,12 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         eng.check_fault()
-        # One graph for the whole step (the NCCL all-reduce is capturable); CVAE_SPLIT_GRAPH=1 keeps the all-reduce
-        # outside, between a forward/backward graph and an Adam graph.
-        if os.environ.get("CVAE_SPLIT_GRAPH") is None:
+        # Single GPU: one graph for the whole step.  Data parallel: the NCCL all-reduce stays OUTSIDE graph capture,
+        # between a forward/backward graph and an Adam graph (capturing the collective hung an 8-rank run on this
+        # pool; CVAE_CAPTURE_ALLREDUCE=1 opts back in, CVAE_SPLIT_GRAPH=1 forces the split on one GPU too).
+        single = (self.world == 1 and os.environ.get("CVAE_SPLIT_GRAPH") is None) or \
+                 (self.world > 1 and os.environ.get("CVAE_CAPTURE_ALLREDUCE") is not None)
+        if single:
             g_front, g_back = torch.cuda.CUDAGraph(), None
             with torch.cuda.graph(g_front):
                 self._eager(from_u8)
