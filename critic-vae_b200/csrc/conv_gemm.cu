@@ -9,18 +9,18 @@
 //
 // Pipeline (conv_pipe_kernel, one persistent CTA per SM, 10 warps):
 //   warps 4-7  plane producers: cp.async 16-byte copies global -> plane buffer (zero-fill for the
-//              padding), two buffers, one (pixel chunk, channel group) each
+//              padding), two buffers, one (pixel chunk, channel group) each; the two fp32 NCHW sources
+//              (frames for encoder conv 0, d_recon * tanh' for decoder conv 4's data gradient) are
+//              converted to bf16 by the producer threads themselves
 //   warp  8    weight producer: cp.async.bulk of packed K-step blocks into a deep mbarrier ring
-//              (the ring has to cover L2 latency x 64/tm bytes per clock)
+//              (stages as large as fit: the MMA thread pays a fixed cost per stage)
 //   warp  9    one elected thread issues tcgen05.mma: `tm` 128-pixel tiles share every weight stage,
 //              their accumulators sit side by side in TMEM; two accumulator sets alternate
 //   warps 0-3  epilogue: tcgen05.ld -> bias / activation / BatchNorm statistics / ReLU mask ->
 //              global, overlapped with the MMAs of the next work item
 // Work item = (pixel chunk of tm*128 virtual pixels, N block); channel groups of <= 128 channels
 // are accumulated into the same TMEM tile so the plane buffers stay <= ~80 KB each.
-//
-// conv_gemm_kernel (the first, phase-sequential version) remains for the two loaders that convert
-// fp32 NCHW tensors on the fly (frames, d_recon) and therefore cannot use cp.async.
+// Encoder conv 0 (3 -> 8 padded channels) uses a paired-tap K order: 13 K = 16 steps cover the 25 taps.
 //
 // Reference ops replaced: nn.Conv2d(5,1,2) at vae_nets.py:69,74,79,84,117,121,125,129,133, the
 // nn.Upsample(2) at :119,123,127,131 (folded: conv5x5(up2(x)) == depth_to_space(conv3x3_4C(x)))
@@ -64,32 +64,6 @@ struct ConvArgs {
     int dbg_flags;            // experiments: 1 = skip epilogue work, 2 = fill planes only once per buffer
     unsigned long long* dbg;  // optional per-CTA cycle counters [grid][8] (cvae_conv_debug_counters)
 };
-
-// K-step table entry: x = byte offset of the A tile inside the plane buffer, y = LBO (bytes)
-__device__ __forceinline__ uint2 ktab_entry(const ConvArgs& a, int i) {
-    uint2 e;
-    if (a.ktab_mode == CVAE_KTAB_GENERIC) {
-        const int cpairs = a.planes >> 1;
-        const int tap = i / cpairs, cp = i - tap * cpairs;
-        const int dy = tap / a.KW - a.pad, dx = tap % a.KW - a.pad;
-        e.x = (uint32_t)(a.halo + dy * a.PW + dx) * 16u + (uint32_t)cp * 2u * a.plane_stride;
-        e.y = (uint32_t)a.plane_stride;
-    } else {  // PAIR8: 5x5 taps of an 8-channel source, two taps per K step
-        if (i < 10) {
-            const int ky = i >> 1, kx = (i & 1) * 2;
-            e.x = (uint32_t)(a.halo + (ky - 2) * a.PW + (kx - 2)) * 16u;
-            e.y = 16u;
-        } else if (i < 12) {
-            const int ky = (i - 10) * 2;
-            e.x = (uint32_t)(a.halo + (ky - 2) * a.PW + 2) * 16u;
-            e.y = (uint32_t)a.PW * 16u;
-        } else {
-            e.x = (uint32_t)(a.halo + 2 * a.PW + 2) * 16u;
-            e.y = 16u;
-        }
-    }
-    return e;
-}
 
 // --------------------------------------------------------------------------------------------
 // epilogue of one 128-pixel tile: warp w owns TMEM lanes [32w, 32w+32) = rows of the tile
@@ -533,146 +507,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvAr
 }
 
 // --------------------------------------------------------------------------------------------
-// phase-sequential kernel (fp32 NCHW loaders): load planes -> MMA -> epilogue per pass
-// --------------------------------------------------------------------------------------------
-static constexpr int kThreads = 192;  // warps 0-3: loader + epilogue, 4: weight producer, 5: MMA
-
-template <int LOADER, int EPI, int N>
-__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int kSeqStages = 6;
-    __shared__ uint64_t bar_full[kSeqStages], bar_empty[kSeqStages], bar_acc;
-    __shared__ uint32_t tmem_slot;
-    __shared__ float stat_scratch[(EPI == CVAE_EPI_STATS) ? 4 * 32 * 17 : 1];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nb = blockIdx.y;
-    const uint32_t stage_bytes = (uint32_t)a.ksps * N * 32;
-
-    uint8_t* planes = smem;
-    uint8_t* wring = smem + (((size_t)a.planes * a.plane_stride + 1023) & ~(size_t)1023);
-    uint2* ktab = reinterpret_cast<uint2*>(wring + (size_t)a.nstages * stage_bytes);
-
-    if (tid == 0) {
-        for (int s = 0; s < a.nstages; ++s) {
-            mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 1);
-        }
-        mbar_init(&bar_acc, 1);
-        mbar_fence_init();
-    }
-    uint32_t ncols = 32;
-    while (ncols < (uint32_t)(a.tm * N)) ncols <<= 1;
-    if (warp == 0) tmem_alloc(&tmem_slot, ncols);
-    for (int i = tid; i < a.ksteps; i += kThreads) ktab[i] = ktab_entry(a, i);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
-    const uint32_t idesc = umma_idesc_bf16(N, kMajorK, kMajorK);
-    const __nv_bfloat16* wsrc = a.wpack + (size_t)nb * a.ksteps * N * 16;
-    const int stages_per_chunk = a.ksteps / a.ksps;
-
-    uint32_t ring_stage = 0, ring_phase = 0;  // producer and MMA thread walk the ring in lock step
-    uint32_t acc_phase = 0;
-    bool alive = true;
-
-    float s1[(EPI == CVAE_EPI_STATS) ? N / 16 : 1], s2[(EPI == CVAE_EPI_STATS) ? N / 16 : 1];
-#pragma unroll
-    for (int g = 0; g < ((EPI == CVAE_EPI_STATS) ? N / 16 : 1); ++g) s1[g] = s2[g] = 0.f;
-
-    for (int chunk = blockIdx.x; chunk < a.num_chunks; chunk += gridDim.x) {
-        const int v0 = a.pad * a.PW + chunk * a.tm * 128;  // first output pixel of this pass
-        fill_planes<LOADER>(a.ps, planes, a.plane_stride, v0 - a.halo, a.L, tid, kThreads);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-
-        if (warp == 4) {
-            if (elect_one()) {
-                for (int st = 0; st < stages_per_chunk && alive; ++st) {
-                    alive = mbar_wait(&bar_empty[ring_stage], ring_phase ^ 1, a.fault);
-                    mbar_expect_tx(&bar_full[ring_stage], stage_bytes);
-                    bulk_g2s(wring + (size_t)ring_stage * stage_bytes,
-                             reinterpret_cast<const uint8_t*>(wsrc) + (size_t)st * stage_bytes, stage_bytes,
-                             &bar_full[ring_stage]);
-                    if (++ring_stage == (uint32_t)a.nstages) { ring_stage = 0; ring_phase ^= 1; }
-                }
-            }
-            __syncwarp();
-        } else if (warp == 5) {
-            if (elect_one()) {
-                const uint32_t planes_addr = smem_u32(planes);
-                const uint32_t wring_addr = smem_u32(wring);
-                for (int st = 0; st < stages_per_chunk && alive; ++st) {
-                    alive = mbar_wait(&bar_full[ring_stage], ring_phase, a.fault);
-                    tc_fence_after();
-                    const uint32_t wb = wring_addr + ring_stage * stage_bytes;
-                    for (int ks = 0; ks < a.ksps; ++ks) {
-                        const int kidx = st * a.ksps + ks;
-                        const uint2 e = ktab[kidx];
-                        uint64_t da = smem_desc(planes_addr + e.x, e.y, 128u);
-                        const uint64_t db = smem_desc(wb + (uint32_t)ks * N * 32u, 128u, 256u);
-                        const uint32_t accumulate = kidx > 0 ? 1u : 0u;
-                        uint32_t tcol = tmem_base;
-#pragma unroll 4
-                        for (int t = 0; t < a.tm; ++t) {
-                            umma_bf16(tcol, da, db, idesc, accumulate);
-                            da += 128;
-                            tcol += N;
-                        }
-                    }
-                    umma_commit(&bar_empty[ring_stage]);
-                    if (++ring_stage == (uint32_t)a.nstages) { ring_stage = 0; ring_phase ^= 1; }
-                }
-                umma_commit(&bar_acc);
-            }
-            __syncwarp();
-        } else {
-            mbar_wait(&bar_acc, acc_phase, a.fault);
-            tc_fence_after();
-            for (int t = 0; t < a.tm; ++t)
-                epilogue_tile<EPI, N>(a, tmem_base + (uint32_t)(t * N), v0 + t * 128, nb, warp, lane, s1, s2, stat_scratch);
-            acc_phase ^= 1;
-        }
-        tc_fence_before();
-        __syncthreads();  // accumulators drained, planes and ring quiescent: next pass may overwrite
-        tc_fence_after();
-    }
-
-    if (warp < 4) flush_stats<EPI, N>(a, nb, lane, s1, s2);
-    if (warp == 0) tmem_free(tmem_base, ncols);
-}
-
-// --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
 static const bool g_debug = getenv("CVAE_DEBUG") != nullptr;
 static unsigned long long* g_dbg_counters = nullptr;
-
-template <int LOADER, int EPI, int N>
-static int launch_seq(const ConvArgs& a, size_t smem, cudaStream_t stream) {
-    auto kern = conv_gemm_kernel<LOADER, EPI, N>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        CVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    uint32_t ncols = 32;
-    while (ncols < (uint32_t)(a.tm * N)) ncols <<= 1;
-    int per_sm = (int)((228 * 1024) / (smem + 2048));
-    if (per_sm > (int)(512 / ncols)) per_sm = (int)(512 / ncols);
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
-    int gx = sm_count() * per_sm / a.n_blocks;
-    if (gx < 1) gx = 1;
-    if (gx > a.num_chunks) gx = a.num_chunks;
-    dim3 grid(gx, a.n_blocks);
-    kern<<<grid, kThreads, smem, stream>>>(a);
-    CVAE_LAUNCH_CHECK();
-    return CVAE_OK;
-}
 
 template <int LOADER, int EPI, int N, int KW>
 static int launch_pipe(const ConvArgs& a, size_t smem, cudaStream_t stream) {
@@ -708,49 +546,6 @@ extern "C" void cvae_conv_debug_counters(void* device_buf) { g_dbg_counters = (u
 extern "C" int cvae_conv_ksteps(int ksize, int src_channels, int ktab) {
     if (ktab == CVAE_KTAB_PAIR8) return 13;
     return ksize * ksize * (src_channels / 16);
-}
-
-static int conv_sequential(const cvae_conv_desc* d, ConvArgs& a, cudaStream_t stream) {
-    const int N = a.nb_pack;
-    a.n_blocks = d->n_total / N;
-    a.planes = d->src_channels / 8;
-    a.ncg = 1;
-    a.kpg = a.ksteps;
-    if (d->ktab == CVAE_KTAB_PAIR8) a.ksps = 13;
-    else {
-        a.ksps = d->src_channels / 16;  // one tap
-        while (a.ksps * N * 32 > 8 * 1024 && a.ksps % 2 == 0) a.ksps /= 2;
-    }
-    CVAE_REQUIRE(a.ksteps % a.ksps == 0, CVAE_EINVAL, "conv_gemm: internal stage split");
-    const size_t stage_bytes = (size_t)a.ksps * N * 32;
-    const long total_v = (long)a.B * a.IH * a.PW - (long)a.pad * a.PW;
-    const int total_tiles = (int)((total_v + 127) / 128);
-    auto smem_for = [&](int tm, int nstages) {
-        const size_t L = (size_t)tm * 128 + 2 * a.halo + 8;
-        return (((size_t)a.planes * L * 16 + 1023) & ~(size_t)1023) + nstages * stage_bytes + (size_t)a.ksteps * 8 + 64;
-    };
-    int tm = d->tm > 0 ? d->tm : (256 / N > 0 ? 256 / N : 1);
-    if (tm > 8) tm = 8;
-    if (tm > total_tiles) tm = total_tiles;
-    a.nstages = 3;
-    const size_t two_per_sm = 112 * 1024, one_per_sm = 200 * 1024;
-    if (d->tm <= 0)
-        while (tm > 1 && smem_for(tm, 3) > two_per_sm) --tm;
-    while (tm > 1 && (smem_for(tm, a.nstages) > one_per_sm || tm * N > 512)) --tm;
-    CVAE_REQUIRE(smem_for(tm, a.nstages) <= one_per_sm && tm * N <= 512, CVAE_EINVAL, "conv_gemm: shape does not fit shared memory");
-    a.tm = tm;
-    a.L = tm * 128 + 2 * a.halo + 8;
-    a.plane_stride = a.L * 16;
-    const size_t smem = smem_for(tm, a.nstages);
-    a.num_chunks = (total_tiles + a.tm - 1) / a.tm;
-    CVAE_REQUIRE((size_t)a.planes * a.plane_stride < (1u << 18), CVAE_EINVAL, "conv_gemm: planes exceed descriptor range");
-#define CVAE_CASE(L_, E_, N_) \
-    if (d->loader == (L_) && d->epilogue == (E_) && N == (N_)) return launch_seq<L_, E_, N_>(a, smem, stream);
-    CVAE_CASE(CVAE_LOAD_NCHW3, CVAE_EPI_STATS, 32)
-    CVAE_CASE(CVAE_LOAD_S2D_NCHW3_DTANH, CVAE_EPI_MASK, 32)
-#undef CVAE_CASE
-    set_error("conv_gemm: no sequential kernel for loader %d epilogue %d N %d", d->loader, d->epilogue, N);
-    return CVAE_EINVAL;
 }
 
 // Tiling policy of the pipelined kernel for one (channel-group size, weight-stage size) choice; fails with
@@ -870,8 +665,6 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     a.ps = PlaneSrc{a.B, a.H, a.W, a.pad, a.PW, a.IH, all_planes,
                     (d->loader == CVAE_LOAD_S2D) ? d->src_channels / 4 : d->src_channels, 0, d->src, d->src2};
 
-    if (getenv("CVAE_SEQ_FP32") && (d->loader == CVAE_LOAD_NCHW3 || d->loader == CVAE_LOAD_S2D_NCHW3_DTANH))
-        return conv_sequential(d, a, stream);
 
     // ---- tiling policy of the pipelined kernel: largest channel groups (fewest plane refills, longest contiguous
     // weight runs) and weight stages that fit; tools/conv_bench.py sweeps showed 16-plane groups and 32 KB stages

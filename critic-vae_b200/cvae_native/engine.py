@@ -47,9 +47,6 @@ def msssim_window():
     return (ctypes.c_float * 11)(*[float(v) for v in k])
 
 
-_SKIP_WGRAD = os.environ.get("CVAE_SKIP_WGRAD") is not None
-
-
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -268,8 +265,6 @@ class VAEEngine:
 
     # ---- backward -----------------------------------------------------------------------------
     def _wgrad(self, g, name, **kw):
-        if _SKIP_WGRAD:     # timing experiment only (CVAE_SKIP_WGRAD=1): how long is the step without weight gradients?
-            return
         d = L.WgradDesc(**{k: (_ptr(v) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
         need = int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d)))
         # one split-K workspace per layer: the fold of one layer overlaps the GEMM of the next
