@@ -43,6 +43,17 @@ def addr_matrix(rows, ksteps, op, hyp):
         else:
             rel = (kk // 8) * lbo + (kk % 8) * 16 + (r // 8) * sbo + (r % 8) * 2
     lin = start + rel
+    if op["swz"] == 64:   # 64-byte swizzle (untested hypothesis, round 2): 16-byte chunk index (2 bits) ^= address bits 7-8
+        if op["major"] == K_MAJOR:
+            rel = (r // 8) * sbo + (r % 8) * 64 + kk * 2
+        else:
+            rel = (kk // 8) * sbo + (kk % 8) * 64 + (r // 32) * lbo + (r % 32) * 2
+        lin = start + rel
+        if hyp["xor"] == "abs":
+            lin = lin ^ (((lin >> 7) & 3) << 4)
+        elif hyp["xor"] == "rel":
+            lin = start + (rel ^ (((rel >> 7) & 3) << 4))
+        return lin
     if op["swz"] and hyp["xor"] == "abs":
         lin = lin ^ (((lin >> 7) & 7) << 4)
     elif op["swz"] and hyp["xor"] == "rel":
@@ -59,7 +70,7 @@ def run_case(name, n, ksteps, a, b, log):
     out = torch.zeros(128, n, dtype=torch.float32, device="cuda")
     rc = lib.probe_run_swz(a_dev.data_ptr(), a["bytes"], b_dev.data_ptr(), b["bytes"], a["off"], b["off"], a["lbo"], a["sbo"], b["lbo"],
                            b["sbo"], a["kstep"], b["kstep"], ksteps, idesc(n, a["major"], b["major"]), n, 0, out.data_ptr(),
-                           2 if a["swz"] else 0, 2 if b["swz"] else 0, a.get("boff", 0), b.get("boff", 0))
+                           {0: 0, 1: 2, 128: 2, 64: 4}[a["swz"]], {0: 0, 1: 2, 128: 2, 64: 4}[b["swz"]], a.get("boff", 0), b.get("boff", 0))
     got = out.cpu().numpy().astype(np.float64)
     res = []
     for swap_a in (False, True):
@@ -113,6 +124,14 @@ def main():
                 a = dict(bytes=2 * blk, major=MN_MAJOR, off=0, lbo=blk, sbo=1024, kstep=2048, swz=1, boff=0)
                 b = dict(bytes=(n // 64) * blk, major=MN_MAJOR, off=shift * 128, lbo=blk, sbo=1024, kstep=2048, swz=1, boff=boff)
                 run_case(f"mnmajor_sw128_AB_n{n}_Bshift{shift}_boff{boff}", n, 4, a, b, log)
+    # 4. (round-2 groundwork, not yet run) 64-byte swizzle for the 32-channel operands: MN-major, 64-byte rows = 32
+    #    channels, 8-row atoms of 512 B (SBO), four column blocks for M = 128, a K = 16 step is 1024 B; B shifted by rows
+    KR = 64 + 32
+    blk64 = KR * 64
+    for shift in (0, 8, 3, 13):
+        a = dict(bytes=4 * blk64, major=MN_MAJOR, off=0, lbo=blk64, sbo=512, kstep=1024, swz=64, boff=0)
+        b = dict(bytes=2 * blk64, major=MN_MAJOR, off=shift * 64, lbo=blk64, sbo=512, kstep=1024, swz=64, boff=0)
+        run_case(f"mnmajor_sw64_AB_n64_Bshift{shift}", 64, 4, a, b, log)
     return 0
 
 
