@@ -175,3 +175,30 @@ def test_data_parallel_plumbing_gloo_world2():
         gs = [(data[s] * (data[s] @ w)[:, None]).mean(0) for s in (idx[:per], idx[per:2 * per])]
         O.adam_step(w, (gs[0] + gs[1]) / 2, m, v, step + 1)
     assert torch.allclose(w, w0, atol=1e-7)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in cvae_native/binding.py must have the size and field offsets gcc gives the structs
+    of include/cvae.h (a maintainer binding the library from another language relies on the header)."""
+    import ctypes
+    import shutil
+    import subprocess
+    import cvae_native.binding as L
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = [("cvae_conv_desc", L.ConvDesc), ("cvae_wgrad_desc", L.WgradDesc), ("cvae_pack_job", L.PackJob)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "cvae.h")}"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
