@@ -1,6 +1,10 @@
 // Weight-gradient GEMM on tcgen05:  acc_g[m][n] = sum_v A[v + a_g][m] * B[v + b_g][n],  K = pixels.
 //
-// Both operands are halo planes ([channel/8][virtual pixel][8 ch], see planes.cuh) read MN-major:
+// Two operand layouts, one GEMM structure:
+//   conv_wgrad_tma_kernel (further down): layers with >= 64 channels on both operands; 128-byte-swizzled
+//                          MN-major tiles written by TMA boxes of the NHWC tensors.
+//   conv_wgrad_kernel    : everything else (32-channel and fp32 sources).  Both operands are halo planes
+// ([channel/8][virtual pixel][8 ch], see planes.cuh) read MN-major:
 // the 16 bytes of a pixel slot are 8 M/N elements and consecutive pixel slots are K.  One
 // accumulator group per filter tap, all groups side by side in TMEM (up to 512 columns), each
 // group being the same B tile read through a descriptor shifted by the tap offset.
