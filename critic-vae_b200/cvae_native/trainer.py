@@ -21,6 +21,15 @@ from . import binding as L
 from .engine import VAEEngine
 
 
+def shard_batch(idx, rank, world):
+    """This rank's contiguous slice of one global batch of sample indices.  Every rank gets the SAME number of
+    samples (the gradient all-reduce weights ranks equally and every rank has to reach it): up to world-1 samples of
+    a batch that does not divide evenly are dropped, and a batch smaller than the world yields an empty slice on
+    EVERY rank (callers skip it together)."""
+    per = len(idx) // world
+    return idx[rank * per:(rank + 1) * per]
+
+
 class TrainStep:
     """Static-buffer training step.  Feed inputs with `load_*`, run with `run()`."""
 

@@ -23,7 +23,7 @@ torch.manual_seed(0)
 from vae_parameters import *  # noqa: E402,F401,F403
 from vae_nets import *  # noqa: E402,F401,F403
 from vae_utility import *  # noqa: E402,F401,F403
-from cvae_native.trainer import TrainStep  # noqa: E402
+from cvae_native.trainer import TrainStep, shard_batch  # noqa: E402
 
 
 def _dist():
@@ -52,9 +52,8 @@ def train(autoencoder, dset, logger=None, critic=None):
         order = torch.as_tensor(seed_rng.permutation(num_samples), device=data.device)
         for batch_i in range(0, num_samples, batch_size):
             idx = order[batch_i:batch_i + batch_size]          # the last, shorter batch is kept (vae.py:44-46)
-            per = (idx.numel() + world - 1) // world
-            idx = idx[rank * per:(rank + 1) * per]
-            if idx.numel() == 0:                               # tail smaller than the world: everyone skips it
+            idx = shard_batch(idx, rank, world)                # same count on every rank; an empty slice is empty everywhere
+            if idx.numel() == 0:
                 continue
             B = idx.numel()
             st = steps.get(B)

@@ -133,8 +133,8 @@ def _dp_worker(rank, world, port, out):
     seen, m, v = [], torch.zeros(64), torch.zeros(64)
     for step, b0 in enumerate(range(0, 40, 16)):           # global batch 16, last one short (8)
         idx = order[b0:b0 + 16]
-        per = (idx.numel() + world - 1) // world
-        mine = idx[rank * per:(rank + 1) * per]
+        from cvae_native.trainer import shard_batch
+        mine = shard_batch(idx, rank, world)                 # the rule vae.py's train() uses
         seen += mine.tolist()
         g_local = (data[mine] * (data[mine] @ w)[:, None]).mean(0) if mine.numel() else torch.zeros(64)
         flat = g_local.clone()
@@ -175,6 +175,15 @@ def test_data_parallel_plumbing_gloo_world2():
         gs = [(data[s] * (data[s] @ w)[:, None]).mean(0) for s in (idx[:per], idx[per:2 * per])]
         O.adam_step(w, (gs[0] + gs[1]) / 2, m, v, step + 1)
     assert torch.allclose(w, w0, atol=1e-7)
+
+
+def test_shard_batch_gives_every_rank_the_same_count():
+    from cvae_native.trainer import shard_batch
+    idx = torch.arange(13)
+    parts = [shard_batch(idx, r, 4) for r in range(4)]
+    assert [p.numel() for p in parts] == [3, 3, 3, 3] and torch.equal(torch.cat(parts), torch.arange(12))
+    assert all(shard_batch(torch.arange(3), r, 4).numel() == 0 for r in range(4))      # smaller than the world: all skip
+    assert torch.equal(shard_batch(idx, 0, 1), idx)
 
 
 def test_ctypes_structs_match_the_c_header(tmp_path):
