@@ -93,7 +93,7 @@ enum cvae_wgrad_kind {
 typedef struct {
     int32_t kind, batch, height, width;
     int32_t cout, cin;           /* reference weight shape [cout][cin][5][5] */
-    int32_t splits;              /* split-K factor, 0 = automatic */
+    int32_t splits;              /* split-K factor, 0 = automatic (a hint: the TMA-fed variant always sizes its own) */
     const void* x;
     const void* dy;
     const void* dy2;
