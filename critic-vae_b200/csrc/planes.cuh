@@ -111,9 +111,12 @@ __device__ __forceinline__ void fill_planes_async(const PlaneSrc& a, const FastD
     }
 }
 
+// Synchronous plane fill for the two fp32 NCHW sources (the threads convert to bf16 themselves); the bf16 sources go
+// through fill_planes_async.
 template <int LOADER>
 __device__ __forceinline__ void fill_planes(const PlaneSrc& a, uint8_t* planes, int plane_stride,
                                             int v_first, int count, int tid, int nthreads) {
+    static_assert(LOADER == CVAE_LOAD_NCHW3 || LOADER == CVAE_LOAD_S2D_NCHW3_DTANH, "bf16 sources use fill_planes_async");
 #pragma unroll 2
     for (int j = tid; j < count; j += nthreads) {
         const int v = v_first + j;
@@ -124,40 +127,7 @@ __device__ __forceinline__ void fill_planes(const PlaneSrc& a, uint8_t* planes, 
         const bool valid = (v >= 0) && (vcol < a.W) && (r >= a.pad) && (n < a.B);
         const int h = r - a.pad, w = vcol;
         uint8_t* dst = planes + (size_t)j * 16;
-        if constexpr (LOADER == CVAE_LOAD_NHWC) {
-            const uint4* s = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const __nv_bfloat16*>(a.src) +
-                ((size_t)(n * a.H + h) * a.W + w) * a.src_c);
-            // issue up to 8 independent 16-byte loads before the first store (memory-level parallelism)
-            for (int q0 = 0; q0 < a.planes; q0 += 8) {
-                uint4 val[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    val[i] = (valid && q0 + i < a.planes) ? __ldg(s + q0 + i) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (q0 + i < a.planes) *reinterpret_cast<uint4*>(dst + (size_t)(q0 + i) * plane_stride) = val[i];
-            }
-        } else if constexpr (LOADER == CVAE_LOAD_S2D) {
-            // source [B][2H][2W][C]; plane q <-> (phase ab = q / (C/8), channel chunk q % (C/8))
-            const int cq = a.src_c >> 3;
-            const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a.src);
-            for (int q0 = 0; q0 < a.planes; q0 += 8) {
-                uint4 val[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int q = q0 + i, ab = q / cq, cc = q - ab * cq;
-                    val[i] = make_uint4(0, 0, 0, 0);
-                    if (valid && q < a.planes) {
-                        const size_t pix = ((size_t)(n * 2 * a.H + 2 * h + (ab >> 1)) * (2 * a.W) + 2 * w + (ab & 1));
-                        val[i] = __ldg(reinterpret_cast<const uint4*>(base + pix * a.src_c) + cc);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (q0 + i < a.planes) *reinterpret_cast<uint4*>(dst + (size_t)(q0 + i) * plane_stride) = val[i];
-            }
-        } else if constexpr (LOADER == CVAE_LOAD_NCHW3) {
+        if constexpr (LOADER == CVAE_LOAD_NCHW3) {
             uint4 val = make_uint4(0, 0, 0, 0);
             float c3 = a.ones ? 1.f : 0.f;
             if (valid) {
