@@ -132,6 +132,12 @@ def main():
         a = dict(bytes=4 * blk64, major=MN_MAJOR, off=0, lbo=blk64, sbo=512, kstep=1024, swz=64, boff=0)
         b = dict(bytes=2 * blk64, major=MN_MAJOR, off=shift * 64, lbo=blk64, sbo=512, kstep=1024, swz=64, boff=0)
         run_case(f"mnmajor_sw64_AB_n64_Bshift{shift}", 64, 4, a, b, log)
+    # 5. (round-2 groundwork, not yet run) conv forward with the weights as A: A = canonical no-swizzle K-major
+    #    (the packed weight blocks), B = K-major 128B-swizzled pixel tile, N = 256 pixels, start shifted by `shift` rows
+    for n in (128, 256):
+        for shift in (0, 3, 11):
+            b = dict(bytes=(n + 32) * 128, major=K_MAJOR, off=shift * 128, lbo=16, sbo=1024, kstep=32, swz=1, boff=0)
+            run_case(f"weightsA_kmajor_sw128_B_n{n}_shift{shift}", n, 4, canon_k(128, 4), b, log)
     return 0
 
 
