@@ -1,6 +1,9 @@
 // Library-wide plumbing: error text, device properties, the device-side fault flag.
 #include <stdarg.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace cvae {
@@ -28,6 +31,23 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// Dynamic shared-memory opt-in.  cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (function, device), not
+// of the calling thread: the cache is process-wide, keyed by both, only ever raised, and guarded by a mutex, so
+// PyTorch's autograd thread and the main thread (or two batch sizes) can never lower each other's setting.
+int opt_in_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::unordered_map<unsigned long long, size_t> configured;
+    int dev = 0;
+    CVAE_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = configured[((unsigned long long)(uintptr_t)func << 6) ^ (unsigned long long)(dev & 63)];
+    if (bytes > have) {
+        CVAE_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return CVAE_OK;
 }
 
 __device__ int g_fault_flag = 0;

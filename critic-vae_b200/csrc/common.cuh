@@ -63,6 +63,12 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+int opt_in_smem(const void* func, size_t bytes);  // api.cu: raise a kernel's dynamic shared-memory limit (process-wide, per device)
+#define CVAE_OPT_IN_SMEM(kern, bytes)                                                    \
+    do {                                                                                 \
+        int rc__ = cvae::opt_in_smem(reinterpret_cast<const void*>(kern), (bytes));      \
+        if (rc__ != CVAE_OK) return rc__;                                                \
+    } while (0)
 int sm_count();     // cached multiprocessor count of the current device (api.cu)
 int* fault_flag();  // device address of the pipeline-fault flag (api.cu)
 

@@ -510,16 +510,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvAr
 // host side
 // --------------------------------------------------------------------------------------------
 static const bool g_debug = getenv("CVAE_DEBUG") != nullptr;
+// experiment switches, read once at load time (never on the launch path)
+static const int g_rotate = getenv("CVAE_NO_ROTATE") ? 0 : 1;
+static const int g_dbg_flags = getenv("CVAE_DBG_FLAGS") ? atoi(getenv("CVAE_DBG_FLAGS")) : 0;
 static unsigned long long* g_dbg_counters = nullptr;
 
 template <int LOADER, int EPI, int N, int KW>
 static int launch_pipe(const ConvArgs& a, size_t smem, cudaStream_t stream) {
     auto kern = conv_pipe_kernel<LOADER, EPI, N, KW>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        CVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    CVAE_OPT_IN_SMEM(kern, smem);
     const int items = a.num_chunks * a.n_blocks;
     int gx = sm_count();
     if (gx > items) gx = items;
@@ -611,7 +610,7 @@ static int plan_pipe(const cvae_conv_desc* d, ConvArgs& a, int all_planes, int m
     const int G = a.planes / 2;
     const int run = (a.ncg == 1 || d->ktab == CVAE_KTAB_PAIR8) ? a.kpg : G;  // contiguous K steps in global memory
     CVAE_REQUIRE((G & (G - 1)) == 0, CVAE_EINVAL, "conv_gemm: channel pairs per group must be a power of two");
-    a.rotate = getenv("CVAE_NO_ROTATE") ? 0 : 1;
+    a.rotate = g_rotate;
     a.kgroup = (G % 4 == 0) ? 4 : (G % 2 == 0 ? 2 : 1);
     while (a.kgroup > 1 && (size_t)a.kgroup * N * 32 > stage_cap) a.kgroup /= 2;
     a.ksps = a.kgroup;
@@ -659,7 +658,7 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     a.bias = d->bias; a.act = (const __nv_bfloat16*)d->act; a.stats = d->stats;
     a.fault = fault_flag();
     a.dbg = g_dbg_counters;
-    a.dbg_flags = getenv("CVAE_DBG_FLAGS") ? atoi(getenv("CVAE_DBG_FLAGS")) : 0;
+    a.dbg_flags = g_dbg_flags;
     CVAE_REQUIRE(a.fault != nullptr, CVAE_ECUDA, "conv_gemm: fault flag unavailable");
     const int all_planes = d->src_channels / 8;
     a.ps = PlaneSrc{a.B, a.H, a.W, a.pad, a.PW, a.IH, all_planes,

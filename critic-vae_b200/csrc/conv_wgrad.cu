@@ -26,6 +26,11 @@
 namespace cvae {
 
 static constexpr int kMaxGroups = 28;
+// experiment switches, read once at load time (never on the launch path)
+static const bool g_wg_debug = getenv("CVAE_DEBUG") != nullptr;
+static const bool g_wg_no_tma = getenv("CVAE_WG_NO_TMA") != nullptr;
+static const int g_wg_kc = getenv("CVAE_WG_KC") ? atoi(getenv("CVAE_WG_KC")) : 0;
+static const int g_fold_linear = getenv("CVAE_FOLD_LINEAR") ? 1 : 0;
 // warps 0 .. kWgLoadWarps-1 load planes (the address arithmetic of a 16-byte-granular gather is latency bound with
 // one warp per scheduler, so there are several per scheduler); warps 0-3 also run the epilogue; the last warp issues MMAs
 static constexpr int kWgLoadWarps = 12;
@@ -419,11 +424,7 @@ __global__ void __launch_bounds__(256) wgrad_fold_rows_kernel(const FoldArgs f, 
 template <int LA, int LB>
 static int launch_wgrad(const WgradArgs& a, size_t smem, dim3 grid, cudaStream_t stream) {
     auto kern = conv_wgrad_kernel<LA, LB>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        CVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    CVAE_OPT_IN_SMEM(kern, smem);
     kern<<<grid, kWgThreads, smem, stream>>>(a);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
@@ -662,7 +663,7 @@ static bool encode_map(CUtensorMap* m, const void* base, int channels, int W, in
 static int launch_wgrad_tma(const cvae_wgrad_desc* d, const WgradArgs& base, int n, int gsets, int H, int W, int pad, cudaStream_t stream,
                             int* splits_out) {
     const int mtot = (d->kind == CVAE_WGRAD_5X5) ? d->cout : 4 * d->cout;
-    if (getenv("CVAE_WG_NO_TMA")) return 1;
+    if (g_wg_no_tma) return 1;
     if (!(d->kind == CVAE_WGRAD_5X5 || d->kind == CVAE_WGRAD_PHASE)) return 1;
     if (mtot % 128 != 0 || d->cin % 64 != 0 || d->cin > 256) return 1;
     if (d->kind == CVAE_WGRAD_PHASE && d->cout != 64) return 1;
@@ -674,7 +675,7 @@ static int launch_wgrad_tma(const cvae_wgrad_desc* d, const WgradArgs& base, int
     t.b_blocks = d->cin / 64;
     const bool bias = d->dbias != nullptr;
     const int m_blocks = mtot / 128;
-    int splits = sm_count() / (gsets * m_blocks);
+    int splits = *splits_out;   // in: the most splits the workspace was sized for; out: the number used
     if (splits < 1) splits = 1;
     const size_t cap = 212 * 1024;
     auto plan = [&](int rows_mode, int NB, int RA) -> bool {
@@ -755,12 +756,8 @@ static int launch_wgrad_tma(const cvae_wgrad_desc* d, const WgradArgs& base, int
     }
     t.partial = base.partial; t.fault = base.fault;
     const size_t smem = (size_t)t.nbuf * t.buf_bytes + (t.ones_off ? (size_t)2 * t.ones_stride : 0);
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        CVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    if (getenv("CVAE_DEBUG"))
+    CVAE_OPT_IN_SMEM(conv_wgrad_tma_kernel, smem);
+    if (g_wg_debug)
         fprintf(stderr, "conv_wgrad_tma kind %d %dx%d cout=%d cin=%d: %s NB=%d RA=%d kc=%d nbuf=%d chunks=%d splits=%d gsets=%d mblocks=%d buf=%d smem=%zu\n",
                 d->kind, H, W, d->cout, d->cin, t.rows_mode ? "rows" : "images", t.NB, t.RA, t.kc, t.nbuf, t.num_chunks, splits, gsets, m_blocks,
                 t.buf_bytes, smem);
@@ -780,19 +777,55 @@ static unsigned long long* g_wg_dbg = nullptr;
 // total / wait-for-data; loaders wait-for-buffer / issue / landing wait / chunks; epilogue.
 extern "C" void cvae_wgrad_debug_counters(void* device_buf) { g_wg_dbg = (unsigned long long*)device_buf; }
 
-extern "C" int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d) {
-    if (!d) return -1;
-    // generous upper bound: splits <= 2 * SM count, every group m_total x (n + 16) floats
-    int m_total, n, groups;
+// GEMM shape of one weight-gradient call, shared by the workspace query and the launcher so the two can never
+// disagree: accumulator groups (filter taps + bias pseudo-groups), how they are dealt to CTAs (gsets sets of gpc
+// groups filling the 512 TMEM columns), the floats of one split-K partial, and the largest split count either
+// kernel variant (plane or TMA) will use.
+struct WgShape {
+    int n, ngroups, bias_groups, groups_total, m_blocks, m_rows, m_total, gpc, gsets, max_splits;
+    long split_floats;
+};
+static bool wgrad_shape(const cvae_wgrad_desc* d, WgShape& s) {
     switch (d->kind) {
-        case CVAE_WGRAD_5X5: m_total = d->cout; n = d->cin; groups = 25; break;
-        case CVAE_WGRAD_PHASE: m_total = 4 * d->cout; n = d->cin; groups = 9; break;
-        case CVAE_WGRAD_SHIFT_FRAMES: m_total = 128; n = d->cout; groups = 5; break;
-        case CVAE_WGRAD_SHIFT_PHASE12: m_total = 128; n = d->cin; groups = 8; break;
-        default: return -1;
+        case CVAE_WGRAD_5X5:
+        case CVAE_WGRAD_PHASE: {
+            const int mtot = (d->kind == CVAE_WGRAD_5X5) ? d->cout : 4 * d->cout;
+            s.n = d->cin; s.ngroups = (d->kind == CVAE_WGRAD_5X5) ? 25 : 9; s.bias_groups = d->dbias ? 1 : 0;
+            s.m_blocks = (mtot + 127) / 128; s.m_rows = mtot < 128 ? mtot : 128;
+            break;
+        }
+        case CVAE_WGRAD_SHIFT_FRAMES: s.n = d->cout; s.ngroups = 5; s.bias_groups = 0; s.m_blocks = 1; s.m_rows = 128; break;
+        case CVAE_WGRAD_SHIFT_PHASE12: s.n = d->cin; s.ngroups = 6; s.bias_groups = 2; s.m_blocks = 1; s.m_rows = 128; break;
+        default: return false;
     }
-    if (m_total < 128) m_total = 128;
-    return (int64_t)2 * 160 * ((int64_t)groups * m_total * n + (int64_t)2 * m_total * 16) * 4;
+    if (s.n <= 0 || s.n > 256) return false;
+    s.m_total = s.m_blocks * s.m_rows;
+    s.groups_total = s.ngroups + s.bias_groups;
+    // groups per CTA: fill the 512 TMEM columns (every group is n columns wide; the bias pseudo-groups 16)
+    s.gpc = 512 / s.n;
+    if (s.gpc < 1) s.gpc = 1;
+    while (s.gpc > 1) {   // keep the column total of every set <= 512 including trailing 16-column pseudo-groups
+        bool ok = true;
+        for (int g0 = 0; g0 < s.groups_total && ok; g0 += s.gpc) {
+            int cols = 0;
+            for (int g = g0; g < g0 + s.gpc && g < s.groups_total; ++g) cols += (g < s.ngroups) ? s.n : 16;
+            ok = cols <= 512;
+        }
+        if (ok) break;
+        --s.gpc;
+    }
+    s.gsets = (s.groups_total + s.gpc - 1) / s.gpc;
+    s.gpc = (s.groups_total + s.gsets - 1) / s.gsets;   // same number of sets, balanced
+    s.max_splits = d->splits > 0 ? d->splits : (sm_count() / (s.gsets * s.m_blocks));
+    if (s.max_splits < 1) s.max_splits = 1;
+    s.split_floats = (long)s.ngroups * s.m_total * s.n + (long)s.bias_groups * s.m_total * 16;
+    return true;
+}
+
+extern "C" int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d) {
+    WgShape s;
+    if (!d || !wgrad_shape(d, s)) return -1;
+    return (int64_t)s.max_splits * s.split_floats * 4;   // both kernel variants use <= max_splits splits
 }
 
 extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
@@ -858,26 +891,14 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
     a.dPW = make_fastdiv(PW);
     a.dIH = make_fastdiv(IH);
 
-    // groups per CTA: fill the 512 TMEM columns (every group is n columns wide; the bias pseudo-groups 16)
-    const int bias_groups = (d->kind == CVAE_WGRAD_SHIFT_FRAMES) ? 0 : (d->kind == CVAE_WGRAD_SHIFT_PHASE12 ? 2 : (d->dbias ? 1 : 0));
-    ngroups = (d->kind == CVAE_WGRAD_5X5) ? 25 : (d->kind == CVAE_WGRAD_PHASE ? 9 : (d->kind == CVAE_WGRAD_SHIFT_FRAMES ? 5 : 6));
-    a.groups_total = ngroups + bias_groups;
-    a.gpc = 512 / n;
-    if (a.gpc < 1) a.gpc = 1;
-    while (a.gpc > 1) {   // keep the column total of every set <= 512 including trailing 16-column pseudo-groups
-        bool ok = true;
-        for (int g0 = 0; g0 < a.groups_total && ok; g0 += a.gpc) {
-            int cols = 0;
-            for (int g = g0; g < g0 + a.gpc && g < a.groups_total; ++g) cols += (g < ngroups) ? n : 16;
-            ok = cols <= 512;
-        }
-        if (ok) break;
-        --a.gpc;
-    }
-    const int gsets = (a.groups_total + a.gpc - 1) / a.gpc;
-    a.gpc = (a.groups_total + gsets - 1) / gsets;   // same number of sets, balanced
-    int splits = d->splits > 0 ? d->splits : (sm_count() / (gsets * a.m_blocks));
-    if (splits < 1) splits = 1;
+    WgShape shape;
+    CVAE_REQUIRE(wgrad_shape(d, shape), CVAE_EINVAL, "conv_wgrad: unsupported shape");
+    CVAE_REQUIRE(shape.n == n && shape.m_total == a.m_total && shape.m_blocks == a.m_blocks, CVAE_EINVAL, "conv_wgrad: internal shape mismatch");
+    ngroups = shape.ngroups;
+    a.groups_total = shape.groups_total;
+    a.gpc = shape.gpc;
+    const int gsets = shape.gsets;
+    int splits = shape.max_splits;
 
     // chunk size: the largest multiple of 16 pixels whose double buffer fits, but small enough that every
     // CTA still gets ~4 chunks to pipeline
@@ -887,7 +908,7 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
     int kc_want = (int)(((per_cta + 3) / 4 + kq - 1) / kq * kq);
     if (kc_want < 64) kc_want = 64;
     if (kc_want > 512) kc_want = 512;
-    if (getenv("CVAE_WG_KC")) kc_want = atoi(getenv("CVAE_WG_KC")) / kq * kq;
+    if (g_wg_kc > 0) kc_want = g_wg_kc / kq * kq;
     int kc = kc_want;
     for (;; kc -= kq) {
         CVAE_REQUIRE(kc >= kq, CVAE_EINVAL, "conv_wgrad: shape does not fit shared memory");
@@ -953,18 +974,18 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
     a.fault = fault_flag();
     a.dbg = g_wg_dbg;
     CVAE_REQUIRE(a.fault != nullptr, CVAE_ECUDA, "conv_wgrad: fault flag unavailable");
-    CVAE_REQUIRE((int64_t)splits * a.split_floats * 4 <= cvae_conv_wgrad_workspace_bytes(d), CVAE_EINVAL,
-                 "conv_wgrad: workspace too small");
+    CVAE_REQUIRE((long)a.split_floats == shape.split_floats, CVAE_EINVAL, "conv_wgrad: internal partial size mismatch");
 
     const size_t smem = (size_t)2 * a.buf_bytes;
     dim3 grid(splits, gsets, a.m_blocks);
-    if (getenv("CVAE_DEBUG"))
+    if (g_wg_debug)
         fprintf(stderr, "conv_wgrad kind %d B=%d %dx%d cout=%d cin=%d: n=%d groups=%d gpc=%d gsets=%d mblocks=%d splits=%d kc=%d chunks=%d "
                         "buf=%d B smem=%zu\n", d->kind, d->batch, H, W, d->cout, d->cin, n, a.groups_total, a.gpc, gsets, a.m_blocks, splits,
                 a.kc, a.num_chunks, a.buf_bytes, (size_t)2 * a.buf_bytes);
-    int rc = launch_wgrad_tma(d, a, n, gsets, H, W, pad, stream, &splits);
+    int tma_splits = shape.max_splits;
+    int rc = launch_wgrad_tma(d, a, n, gsets, H, W, pad, stream, &tma_splits);
     if (rc < 0) return rc;
-    if (rc == CVAE_OK) { /* TMA variant launched (splits may differ) */ }
+    if (rc == CVAE_OK) splits = tma_splits;   // TMA variant launched with its own chunking
     else if (la == CVAE_LOAD_NHWC) rc = launch_wgrad<CVAE_LOAD_NHWC, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     else if (la == CVAE_LOAD_S2D) rc = launch_wgrad<CVAE_LOAD_S2D, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     else if (la == CVAE_LOAD_NCHW3) rc = launch_wgrad<CVAE_LOAD_NCHW3, CVAE_LOAD_NHWC>(a, smem, grid, stream);
@@ -980,7 +1001,7 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
         CVAE_REQUIRE(e2 == cudaSuccess, CVAE_ECUDA, "conv_wgrad: fold stream dependency failed: %s", cudaGetErrorString(e2));
         stream = (cudaStream_t)d->fold_stream;
     }
-    f.dbg_linear = getenv("CVAE_FOLD_LINEAR") ? 1 : 0;
+    f.dbg_linear = g_fold_linear;
     f.kind = d->kind; f.cout = d->cout; f.cin = d->cin; f.splits = splits; f.split_floats = a.split_floats;
     f.m_total = a.m_total; f.n = n; f.partial = a.partial; f.dw = (float*)d->dw; f.dbias = (float*)d->dbias;
     {

@@ -117,11 +117,7 @@ extern "C" int cvae_critic_fwd(int frames, const float* x, const float* weights,
     CVAE_REQUIRE(frames >= 0 && (frames == 0 || (x && weights && pred)), CVAE_EINVAL, "critic_fwd: bad argument");
     if (frames == 0) return CVAE_OK;
     const size_t smem = sizeof(float) * (11876 + 3 * 4096 + 8 * 1024 + 8 * 256 + 8 * 64 + 256 + 64);
-    static thread_local bool configured = false;
-    if (!configured) {
-        CVAE_CUDA(cudaFuncSetAttribute(critic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    CVAE_OPT_IN_SMEM(critic_fwd_kernel, smem);
     const int grid = frames < sm_count() ? frames : sm_count();
     critic_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(frames, x, weights, pred);
     CVAE_LAUNCH_CHECK();

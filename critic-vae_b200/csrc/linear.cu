@@ -286,11 +286,7 @@ extern "C" int cvae_fc_fwd(int batch, const void* act, const float* wfc, const f
                            const float* bias_var, float* mu_logvar, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CVAE_REQUIRE(batch > 0 && act && wfc && bias_mu && bias_var && mu_logvar, CVAE_EINVAL, "fc_fwd: bad argument");
-    static thread_local bool configured = false;
-    if (!configured) {
-        CVAE_CUDA(cudaFuncSetAttribute(fc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmem));
-        configured = true;
-    }
+    CVAE_OPT_IN_SMEM(fc_fwd_kernel, kFcSmem);
     int* fault = fault_flag();
     CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "fc_fwd: fault flag unavailable");
     fc_fwd_kernel<<<((batch + kFcRows - 1) / kFcRows) * kFcSplit, 256, kFcSmem, stream>>>(batch, (const __nv_bfloat16*)act, wfc, bias_mu,
@@ -330,11 +326,7 @@ extern "C" int cvae_decin_bwd(int batch, const void* d_out, const float* z_pred,
     CVAE_REQUIRE(batch > 0 && d_out && (d_z_pred || dw || db), CVAE_EINVAL, "decin_bwd: bad argument");
     if (d_z_pred) {
         CVAE_REQUIRE(wdec != nullptr, CVAE_EINVAL, "decin_bwd: data gradient needs the packed weights");
-        static thread_local bool configured = false;
-        if (!configured) {
-            CVAE_CUDA(cudaFuncSetAttribute(decin_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDdSmem));
-            configured = true;
-        }
+        CVAE_OPT_IN_SMEM(decin_bwd_data_kernel, kDdSmem);
         int* fault = fault_flag();
         CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "decin_bwd: fault flag unavailable");
         decin_bwd_data_kernel<<<((batch + kDdRows - 1) / kDdRows) * kDdSplit, 256, kDdSmem, stream>>>(

@@ -333,11 +333,7 @@ extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, cons
     CVAE_REQUIRE(batch > 0 && recon && x && mu_logvar && window11 && sums && coef && losses, CVAE_EINVAL, "loss_fwd: bad argument");
     Window w;
     memcpy(w.g, window11, sizeof(w.g));
-    static thread_local bool configured = false;
-    if (!configured) {
-        CVAE_CUDA(cudaFuncSetAttribute(msssim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms_smem(false)));
-        configured = true;
-    }
+    CVAE_OPT_IN_SMEM(msssim_kernel<false>, ms_smem(false));
     CVAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 10, stream));
     const int planes = batch * 3;
     const int grid = planes < sm_count() ? planes : sm_count();
@@ -356,11 +352,7 @@ extern "C" int cvae_loss_bwd(int batch, const float* recon, const float* x, cons
                  "loss_bwd: bad argument");
     Window w;
     memcpy(w.g, window11, sizeof(w.g));
-    static thread_local bool configured = false;
-    if (!configured) {
-        CVAE_CUDA(cudaFuncSetAttribute(msssim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms_smem(true)));
-        configured = true;
-    }
+    CVAE_OPT_IN_SMEM(msssim_kernel<true>, ms_smem(true));
     const int planes = batch * 3;
     const int grid = planes < sm_count() ? planes : sm_count();
     msssim_kernel<true><<<grid, kMsThreads, ms_smem(true), stream>>>(planes, recon, x, w, nullptr, coef, grad_out, d_recon);

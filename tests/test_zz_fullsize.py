@@ -1,20 +1,39 @@
 """Full-size checks of the CUDA-graph training step (cvae_native.trainer.TrainStep, the path bench.py times) at
-BASELINE.json's batch of 256, through properties that do not need a 256-frame CPU reference run:
+BASELINE.json's batch sizes (configs[1]: batch 256; configs[0]: batch 64 forward + loss), directly against the CPU
+oracle and through properties that need no reference run:
 
-  * tiling invariance: a batch made of 4 copies of 64 frames (and of their eps) has the same BatchNorm statistics,
-    the same batch-global MS-SSIM means, hence the same loss and the same (batch-mean) gradients as the 64-frame batch;
-  * the 64-frame step itself is checked against the CPU oracle (loss rel 1e-3 as in BASELINE.json's north_star).
+  * TrainStep at batch 256 vs oracle: losses (rel 1e-3), every parameter gradient (within the bf16-storage budget),
+    the Adam update, BatchNorm running buffers, for two consecutive optimizer steps (reference loop vae.py:47-58);
+  * the uint8 front end (`from_u8=True` graph) gives the same step as fp32 frames;
+  * tiling invariance: a batch made of 4 copies of 64 frames has the same loss and gradients as the 64-frame batch;
+  * thread regression: the dynamic shared-memory opt-in must survive launches from other host threads.
 
 The file name keeps these tests last in the run."""
+import json
+import os
+import threading
+
 import numpy as np
 import pytest
 import torch
 
 import critic_vae_oracle as O
 import synth
-from test_vae_module import _modules, _rel, LOSS_RTOL
+from test_vae_module import _modules, _rel, LOSS_RTOL, PIXEL_ATOL, LATENT_ATOL, GRAD_BUDGET_FACTOR, GRAD_REL_FLOOR
 
 pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _report(name, payload):
+    """Keep the measured error ratios (profiles/ holds the committed copy of the last GPU run)."""
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
+            json.dump(payload, f, indent=1)
+    except OSError:
+        pass
 
 
 def _graph_step(critic_state, batch, x64, eps64):
@@ -30,6 +49,183 @@ def _graph_step(critic_state, batch, x64, eps64):
     torch.cuda.synchronize()
     st.eng.check_fault()
     return losses.cpu().numpy().astype(np.float64), st.eng.gflat.clone().cpu(), st
+
+
+def _state_dicts(vae):
+    enc = {k: v.detach().cpu().clone() for k, v in vae.encoder.state_dict().items()}
+    dec = {k: v.detach().cpu().clone() for k, v in vae.decoder.state_dict().items()}
+    return enc, dec
+
+
+def _check_grads(eng, gflat, g_ref, g_mod, tag):
+    """Every parameter gradient within GRAD_BUDGET_FACTOR x the bf16-storage budget (or GRAD_REL_FLOOR)."""
+    rows, worst = [], 0.0
+    for name, _ in eng.layout:
+        ref = g_ref[name].double().numpy()
+        got = eng.view(name, gflat).double().cpu().numpy()
+        if np.linalg.norm(ref) < 1e-7:     # conv biases in front of BatchNorm: exactly zero
+            assert np.abs(got).max() == 0.0, name
+            continue
+        rel = _rel(got, ref)
+        budget = _rel(g_mod[name].double().numpy(), ref)
+        rows.append({"param": name, "rel_l2": rel, "bf16_budget": budget, "ratio": rel / max(budget, 1e-12)})
+        assert rel < max(GRAD_BUDGET_FACTOR * budget, GRAD_REL_FLOOR), f"{tag} grad {name}: rel {rel:.3e}, budget {budget:.3e}"
+        if rel > GRAD_REL_FLOOR:
+            worst = max(worst, rel / max(budget, 1e-12))
+    return rows, worst
+
+
+def test_wgrad_smem_opt_in_survives_other_threads():
+    """Regression for the round-1 failure: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per function, not per
+    thread.  Large-smem launch on the main thread, small-smem launch from another thread (as PyTorch's autograd
+    thread does), large again on the main thread: all three must launch and agree with themselves."""
+    import ctypes
+    from cvae_native import binding as L
+
+    def wgrad(B):
+        g = torch.Generator(device="cuda").manual_seed(B)
+        x = torch.randn(B, 32, 32, 32, device="cuda", generator=g).to(torch.bfloat16)
+        dy = torch.randn(B, 32, 32, 64, device="cuda", generator=g).to(torch.bfloat16)
+        dw = torch.zeros(64, 32, 5, 5, device="cuda")
+        d = L.WgradDesc(kind=L.WGRAD_5X5, batch=B, height=32, width=32, cout=64, cin=32, splits=0, x=x.data_ptr(), dy=dy.data_ptr(),
+                        dy2=None, dw=dw.data_ptr(), dbias=None, workspace=None, fold_stream=None)
+        ws = torch.empty(int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d))), dtype=torch.uint8, device="cuda")
+        d.workspace = ws.data_ptr()
+        L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()))
+        torch.cuda.synchronize()
+        return dw
+
+    big0 = wgrad(64)                      # kc = 256 -> ~180 KB of dynamic shared memory
+    err = []
+
+    def other():
+        try:
+            torch.cuda.set_device(0)
+            wgrad(4)                      # kc = 64 -> ~60 KB, from a thread whose caches are cold
+        except Exception as exc:          # noqa
+            err.append(exc)
+
+    t = threading.Thread(target=other)
+    t.start(); t.join()
+    assert not err, err
+    big1 = wgrad(64)
+    assert torch.equal(big0, big1)
+    L.check(L.lib.cvae_check_device_fault(L.stream_ptr()))
+
+
+def test_wgrad_workspace_is_sized_from_the_plan():
+    """The split-K workspace query returns what the launch uses (round 1 over-allocated ~1 GiB per layer)."""
+    import ctypes
+    from cvae_native import binding as L
+    total = 0
+    for kind, h, co, ci in ((L.WGRAD_5X5, 4, 128, 256), (L.WGRAD_5X5, 8, 256, 128), (L.WGRAD_5X5, 16, 128, 64), (L.WGRAD_5X5, 32, 64, 32),
+                            (L.WGRAD_PHASE, 4, 64, 128), (L.WGRAD_PHASE, 8, 32, 64), (L.WGRAD_PHASE, 16, 32, 32),
+                            (L.WGRAD_SHIFT_FRAMES, 64, 32, 3), (L.WGRAD_SHIFT_PHASE12, 32, 3, 32)):
+        d = L.WgradDesc(kind=kind, batch=256, height=h, width=h, cout=co, cin=ci, splits=0, dbias=8)
+        need = int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d)))
+        assert 0 < need <= 160 << 20, (kind, h, co, ci, need)
+        total += need
+    assert total <= 640 << 20, total
+
+
+def test_trainstep_b256_two_steps_vs_oracle(critic_state):
+    """BASELINE.json configs[1]: the CUDA-graph training step at batch 256 against the oracle, two optimizer steps.
+    Step s is differentiated by the oracle at the weights the device step started from."""
+    from cvae_native.trainer import TrainStep
+    B = 256
+    vae, critic = _modules(critic_state)
+    vae.train()
+    st = TrainStep(vae, critic, B)
+    eng = st.eng
+    summary = []
+    m = v = None
+    for s in range(2):
+        x, eps = synth.make_frames(B, seed=80 + s), synth.make_eps(B, seed=90 + s)
+        enc0, dec0 = _state_dicts(vae)
+        flat0 = eng.flat.clone()
+        st.load(frames=x.cuda(), eps=eps.cuda())
+        losses = st.run().clone()
+        torch.cuda.synchronize()
+        eng.check_fault()
+        losses = losses.cpu().numpy().astype(np.float64)
+        g = eng.gflat.clone()
+        pred_ref = O.critic_forward(critic_state, x)
+        np.testing.assert_allclose(st.pred.cpu().numpy(), pred_ref.numpy()[:, 0], atol=5e-6)
+        l_ref, recon_ref, mu_ref, lv_ref, g_ref = O.loss_and_grads(enc0, dec0, x, pred_ref, eps, update_stats=True)
+        _, _, _, _, g_mod = O.loss_and_grads_bf16_storage(enc0, dec0, x, pred_ref, eps)
+        np.testing.assert_allclose(losses[0], l_ref["total_loss"].item(), rtol=LOSS_RTOL)
+        np.testing.assert_allclose(losses[1], l_ref["recon_loss"].item(), rtol=LOSS_RTOL)
+        np.testing.assert_allclose(losses[2], l_ref["KLD"].item(), rtol=2e-2)
+        np.testing.assert_allclose(st.ws.recon.cpu().numpy(), recon_ref.numpy(), atol=PIXEL_ATOL)
+        np.testing.assert_allclose(st.ws.ml[:, :32].cpu().numpy(), mu_ref.numpy(), atol=LATENT_ATOL)
+        np.testing.assert_allclose(st.ws.ml[:, 32:].cpu().numpy(), lv_ref.numpy(), atol=LATENT_ATOL)
+        rows, worst = _check_grads(eng, g, g_ref, g_mod, f"step {s}")
+        # BatchNorm running buffers after the step (enc0 was updated in place by the oracle)
+        for i, bi in enumerate(O.ENC_BN):
+            np.testing.assert_allclose(eng.running_mean[i].cpu().numpy(), enc0[f"model.{bi}.running_mean"].numpy(), atol=2e-3, rtol=1e-3)
+            np.testing.assert_allclose(eng.running_var[i].cpu().numpy(), enc0[f"model.{bi}.running_var"].numpy(), atol=2e-3, rtol=1e-3)
+            assert int(eng.nbt[i].item()) == s + 1
+        # Adam: the fused device update equals torch.optim.Adam's rule applied to the DEVICE gradient
+        p_ref, g_c = flat0.double().cpu(), g.double().cpu()
+        if m is None:
+            m, v = torch.zeros_like(p_ref), torch.zeros_like(p_ref)
+        O.adam_step(p_ref, g_c, m, v, s + 1)
+        np.testing.assert_allclose(eng.flat.double().cpu().numpy(), p_ref.numpy(), atol=2e-7, rtol=0)
+        assert int(eng.step.item()) == s + 1
+        summary.append({"step": s, "loss": losses.tolist(), "loss_ref": [l_ref[k].item() for k in ("total_loss", "recon_loss", "KLD")],
+                        "recon_max_abs": float(np.abs(st.ws.recon.cpu().numpy() - recon_ref.numpy()).max()),
+                        "worst_grad_ratio_to_bf16_budget": worst, "grads": rows})
+    _report("trainstep_b256", summary)
+    print("\n".join(f"step {r['step']}: loss {r['loss'][0]:.6f} vs {r['loss_ref'][0]:.6f}, recon max-abs {r['recon_max_abs']:.2e}, "
+                    f"worst grad err / bf16 budget {r['worst_grad_ratio_to_bf16_budget']:.2f}" for r in summary))
+
+
+def test_trainstep_from_u8_matches_fp32_frames(critic_state):
+    """The uint8 HWC front end (cvae_frames_u8_to_f32 inside the graph) is the same step as fp32 NCHW frames."""
+    from cvae_native.trainer import TrainStep
+    B = 64
+    x = synth.make_frames(B, seed=75)                                    # snapped to k/255
+    u8 = torch.round(x * 255.0).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    eps = synth.make_eps(B, seed=76)
+    out = []
+    for from_u8 in (False, True):
+        vae, critic = _modules(critic_state)
+        vae.train()
+        st = TrainStep(vae, critic, B)
+        if from_u8:
+            st.load(frames_u8=u8.cuda(), eps=eps.cuda())
+        else:
+            st.load(frames=x.cuda(), eps=eps.cuda())
+        losses = st.run(from_u8=from_u8).clone()
+        torch.cuda.synchronize()
+        st.eng.check_fault()
+        if from_u8:
+            assert torch.equal(st.x.cpu(), u8.permute(0, 3, 1, 2).float() / 255.0)      # bit-exact astype(float32) / 255
+        out.append((losses.cpu().numpy(), st.eng.gflat.clone().cpu().numpy(), st.eng.flat.clone().cpu().numpy()))
+    np.testing.assert_allclose(out[1][0], out[0][0], rtol=1e-6)
+    assert _rel(out[1][1], out[0][1]) < 1e-5
+    np.testing.assert_allclose(out[1][2], out[0][2], atol=1e-7)
+
+
+def test_config1_forward_loss_b64_vs_oracle(critic_state):
+    """BASELINE.json configs[0]: forward + recon/KL loss at batch 64 through the drop-in module (vae_nets.py:14-19,53-62)."""
+    B = 64
+    vae, critic = _modules(critic_state)
+    vae.train()
+    x, eps = synth.make_frames(B, seed=77), synth.make_eps(B, seed=78)
+    enc0, dec0 = _state_dicts(vae)
+    preds = critic.evaluate(x.cuda())
+    with torch.no_grad():
+        out = vae(x.cuda(), preds, eps=eps.cuda())
+        losses = vae.vae_loss(*out)
+    vae._engine.check_fault()
+    pred_ref = O.critic_forward(critic_state, x)
+    _, mu, logvar, recon = O.vae_forward(enc0, dec0, x, pred_ref, eps, training=True, update_stats=False)
+    l_ref = O.vae_loss(x, mu, logvar, recon)
+    np.testing.assert_allclose(losses["total_loss"].item(), l_ref["total_loss"].item(), rtol=LOSS_RTOL)
+    np.testing.assert_allclose(losses["recon_loss"].item(), l_ref["recon_loss"].item(), rtol=LOSS_RTOL)
+    np.testing.assert_allclose(losses["KLD"].item(), l_ref["KLD"].item(), rtol=2e-2)
+    np.testing.assert_allclose(out[3].cpu().numpy(), recon.numpy(), atol=PIXEL_ATOL)
 
 
 def test_batch_256_equals_four_copies_of_batch_64(critic_state):
@@ -53,8 +249,9 @@ def test_graph_step_matches_oracle_at_64(critic_state):
     enc, dec = synth.make_vae_state(0)
     pred = O.critic_forward(critic_state, x64)
     l_ref, _, _, _, g_ref = O.loss_and_grads(enc, dec, x64, pred, eps64, update_stats=False)
+    _, _, _, _, g_mod = O.loss_and_grads_bf16_storage(enc, dec, x64, pred, eps64)
     np.testing.assert_allclose(losses[0], l_ref["total_loss"].item(), rtol=LOSS_RTOL)
     np.testing.assert_allclose(losses[1], l_ref["recon_loss"].item(), rtol=LOSS_RTOL)
     np.testing.assert_allclose(losses[2], l_ref["KLD"].item(), rtol=2e-2)
-    got = st.eng.view("decoder.model.12.weight", g).double().numpy()
-    assert _rel(got, g_ref["decoder.model.12.weight"].double().numpy()) < 2e-2
+    rows, worst = _check_grads(st.eng, g.cuda(), g_ref, g_mod, "B=64")
+    _report("trainstep_b64", {"worst_grad_ratio_to_bf16_budget": worst, "grads": rows})

@@ -138,6 +138,15 @@ def main():
         for shift in (0, 3, 11):
             b = dict(bytes=(n + 32) * 128, major=K_MAJOR, off=shift * 128, lbo=16, sbo=1024, kstep=32, swz=1, boff=0)
             run_case(f"weightsA_kmajor_sw128_B_n{n}_shift{shift}", n, 4, canon_k(128, 4), b, log)
+    # 6. the same with 8-row atoms that are NOT contiguous (SBO = 1280: one 8-pixel image row per atom, rows PW = 10 pixels apart)
+    for shift in (0, 1, 11):
+        b = dict(bytes=32 * 1280 + 64 * 128, major=K_MAJOR, off=shift * 128, lbo=16, sbo=1280, kstep=32, swz=1, boff=0)
+        run_case(f"weightsA_kmajor_sw128_B_n256_sbo1280_shift{shift}", 256, 4, canon_k(128, 4), b, log)
+    # 7. 64-byte-swizzled K-major pixel tile (32-channel sources: 64-byte rows, 8-row atoms of 512 B), K = 32 = two steps of 32 B
+    for n in (128, 256):
+        for shift in (0, 3, 11):
+            b = dict(bytes=(n + 32) * 64, major=K_MAJOR, off=shift * 64, lbo=16, sbo=512, kstep=32, swz=64, boff=0)
+            run_case(f"weightsA_kmajor_sw64_B_n{n}_shift{shift}", n, 2, canon_k(128, 2), b, log)
     return 0
 
 
