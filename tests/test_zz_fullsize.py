@@ -234,13 +234,16 @@ def test_batch_256_equals_four_copies_of_batch_64(critic_state):
     l256, g256, st = _graph_step(critic_state, 256, x64, eps64)
     assert np.all(np.isfinite(l256)) and torch.isfinite(g256).all()
     np.testing.assert_allclose(l256, l64, rtol=5e-4, err_msg="loss of the tiled 256 batch vs the 64 batch")
-    # same gradient up to fp32 summation order (split-K partitions differ with the batch size)
+    # same gradient up to fp32 summation order (split-K partitions differ with the batch size) ...
     assert _rel(g256.double().numpy(), g64.double().numpy()) < 1e-2
-    for name in ("decoder.model.12.weight", "decoder.model.0.weight", "encoder.model.8.weight", "encoder.model.0.weight",
-                 "encoder.fc_var.weight", "decoder.decoder_input.weight"):
-        a = st.eng.view(name, g256).double().numpy()
-        b = st.eng.view(name, g64).double().numpy()
-        assert _rel(a, b) < 2e-2, name
+    # ... and, per parameter tensor, the tiled batch is as close to the 64-frame ORACLE gradient as any bf16-operand
+    # implementation can be (the two device runs are two realisations of the bf16 rounding noise, so comparing them
+    # with each other per tensor would need sqrt(2) x the budget; measured 2.3 % on decoder.model.0.weight)
+    enc, dec = synth.make_vae_state(0)
+    pred = O.critic_forward(critic_state, x64)
+    _, _, _, _, g_ref = O.loss_and_grads(enc, dec, x64, pred, eps64, update_stats=False)
+    _, _, _, _, g_mod = O.loss_and_grads_bf16_storage(enc, dec, x64, pred, eps64)
+    _check_grads(st.eng, g256, g_ref, g_mod, "tiled 256 vs oracle 64")
 
 
 def test_graph_step_matches_oracle_at_64(critic_state):
