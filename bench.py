@@ -206,7 +206,9 @@ def latent_secondary(device, hbm_peak):
     eps = torch.randn(N, 32, device=device, generator=g)
     pred = torch.rand(N, device=device, generator=g)
     zc = torch.empty(N, 33, device=device)
-    call = lambda: L.check(L.lib.cvae_latent_fwd(N, 1, ml.data_ptr(), eps.data_ptr(), pred.data_ptr(), zc.data_ptr(), L.stream_ptr()))
+    parts = torch.empty(L.lib.cvae_latent_kld_partials(N), dtype=torch.float64, device=device)
+    call = lambda: L.check(L.lib.cvae_latent_fwd(N, 1, ml.data_ptr(), eps.data_ptr(), pred.data_ptr(), zc.data_ptr(), parts.data_ptr(),
+                                                 L.stream_ptr()))
     for _ in range(3):
         call()
     torch.cuda.synchronize()

@@ -31,6 +31,8 @@
 
 namespace cvae {
 
+int conv_wa_dispatch(const cvae_conv_desc* d, cudaStream_t stream);   // conv_wa.cu
+
 struct ConvArgs {
     int B, H, W, pad, KW;
     int PW, IH;          // W + pad, H + pad
@@ -639,6 +641,7 @@ extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {
     CVAE_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0, CVAE_EINVAL, "conv_gemm: empty shape");
     CVAE_REQUIRE(d->n_total % 16 == 0 && d->n_total > 0, CVAE_EINVAL, "conv_gemm: n_total %d", d->n_total);
     CVAE_REQUIRE(d->src && d->wpack && d->out, CVAE_EINVAL, "conv_gemm: null tensor");
+    if (d->ktab == CVAE_KTAB_BLOCK64) return conv_wa_dispatch(d, stream);
     if (d->ktab == CVAE_KTAB_PAIR8)
         CVAE_REQUIRE(d->src_channels == 8 && d->ksize == 5, CVAE_EINVAL, "conv_gemm: PAIR8 needs 8 channels, 5x5");
     else

@@ -17,11 +17,10 @@
 // 3x3 phase taps of the up-sample-folded decoder convs back onto the 5x5 filter).
 //
 // Replaces autograd's weight/bias gradients of nn.Conv2d at vae_nets.py:69,74,79,84,117-133.
-#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
-
 #include "common.cuh"
 #include "umma.cuh"
 #include "planes.cuh"
+#include "tma.cuh"
 
 namespace cvae {
 
@@ -468,13 +467,6 @@ struct WgTmaArgs {
 
 static constexpr int kWtThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-        : "memory");
-}
-
 __global__ void __launch_bounds__(kWtThreads, 1)
 conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -631,10 +623,7 @@ conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap map
     if (warp == 0) tmem_free(tmem_base, ncols);
 }
 
-typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static TensorMapEncodeFn tensor_map_encoder() {
+TensorMapEncodeFn tensor_map_encoder() {
     static TensorMapEncodeFn fn = nullptr;
     static bool tried = false;
     if (!tried) {
@@ -649,14 +638,7 @@ static TensorMapEncodeFn tensor_map_encoder() {
 
 // bf16 tensor viewed as {channels, w, h, n} with element strides (in elements) for w, h, n; box {64, bw, bh, bn}, SWIZZLE_128B
 static bool encode_map(CUtensorMap* m, const void* base, int channels, int W, int H, int B, long sw, long sh, long sn, int bw, int bh, int bn) {
-    TensorMapEncodeFn enc = tensor_map_encoder();
-    if (!enc) return false;
-    cuuint64_t gdim[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t gstr[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return encode_map_4d(m, base, channels, W, H, B, sw, sh, sn, 64, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // Plans and launches the TMA variant; returns 1 when the shape is not eligible (the caller falls back to the plane kernel).

@@ -196,31 +196,97 @@ __global__ void bn_pool_act_bwd_kernel(int B, int H, int W, int C, int act, cons
 // ---------------------------------------------------------------------------------------------
 // Latent kernel (vae_nets.py:48-51 reparametrize, :143 critic concat) and its backward
 // ---------------------------------------------------------------------------------------------
-__global__ void latent_fwd_kernel(int B, int sample, const float* __restrict__ ml, const float* __restrict__ eps,
-                                  const float* __restrict__ pred, float* __restrict__ zc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * 33) return;
-    const int b = i / 33, d = i - b * 33;
-    float v;
-    if (d == 32) v = pred[b];
-    else {
-        const float mu = ml[b * 64 + d];
-        v = sample ? fmaf(eps[b * 32 + d], expf(0.5f * ml[b * 64 + 32 + d]), mu) : mu;
+// One block = 64 batch rows, 256 threads.  Loads are float4 (a warp covers four rows: 4 x 128 contiguous bytes of mu,
+// of logvar, and 512 contiguous bytes of eps), the 33-float output rows (z | pred, 132 bytes: only 4-byte aligned on
+// their own) are staged in shared memory and leave as one contiguous, 16-byte aligned run of float4 stores.  The KL
+// term of the same mu / logvar (vae_nets.py:57-58: sum(1 + lv - mu^2 - exp(lv))) is reduced with warp shuffles in the
+// same pass; one double partial per block, summed in block order by loss_finalize_kernel (deterministic).
+static constexpr int kLatRows = 64;
+__global__ void __launch_bounds__(256) latent_fwd_kernel(int B, int sample, const float* __restrict__ ml, const float* __restrict__ eps,
+                                                         const float* __restrict__ pred, float* __restrict__ zc,
+                                                         double* __restrict__ kld_partial) {
+    __shared__ __align__(16) float stage[kLatRows * 33];
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * kLatRows;
+    const int rows = (int)min((long long)kLatRows, (long long)B - row0);
+    double kl = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = tid + 256 * k, r = i >> 3, d4 = i & 7;
+        if (r < rows) {
+            const float4* mrow = reinterpret_cast<const float4*>(ml + (row0 + r) * 64);
+            const float4 mu = __ldg(mrow + d4), lv = __ldg(mrow + 8 + d4);
+            float4 z = mu;
+            if (sample) {
+                const float4 e = __ldg(reinterpret_cast<const float4*>(eps + (row0 + r) * 32) + d4);
+                z.x = fmaf(e.x, expf(0.5f * lv.x), mu.x);
+                z.y = fmaf(e.y, expf(0.5f * lv.y), mu.y);
+                z.z = fmaf(e.z, expf(0.5f * lv.z), mu.z);
+                z.w = fmaf(e.w, expf(0.5f * lv.w), mu.w);
+            }
+            float* s = stage + r * 33 + d4 * 4;     // bank (r + 4 d4 + j) % 32: the 32 lanes of a warp hit 32 banks
+            s[0] = z.x; s[1] = z.y; s[2] = z.z; s[3] = z.w;
+            if (kld_partial) {
+                kl += (double)(1.f + lv.x - mu.x * mu.x - expf(lv.x));
+                kl += (double)(1.f + lv.y - mu.y * mu.y - expf(lv.y));
+                kl += (double)(1.f + lv.z - mu.z * mu.z - expf(lv.z));
+                kl += (double)(1.f + lv.w - mu.w * mu.w - expf(lv.w));
+            }
+        }
     }
-    zc[i] = v;
+    if (tid < rows) stage[tid * 33 + 32] = __ldg(pred + row0 + tid);
+    if (kld_partial) {
+        kl = warp_sum(kl);
+        if ((tid & 31) == 0) red[tid >> 5] = kl;
+    }
+    __syncthreads();
+    float* dst = zc + row0 * 33;                    // 64 * 33 * 4 bytes per block: every block starts 16-byte aligned
+    const int n = rows * 33, n4 = n >> 2;
+    for (int i = tid; i < n4; i += 256) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(stage)[i];
+    for (int i = (n4 << 2) + tid; i < n; i += 256) dst[i] = stage[i];
+    if (kld_partial && tid == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w];
+        kld_partial[blockIdx.x] = t;
+    }
 }
 
-// d_ml[b][0:32] = dz + dmu_ext ; d_ml[b][32:64] = dz * eps * 0.5 * exp(0.5 logvar) + dlogvar_ext
+// d_ml[b][0:32] = dz + dmu_ext + k mu ; d_ml[b][32:64] = dz * eps * 0.5 * exp(0.5 logvar) + dlogvar_ext + k 0.5 (exp(logvar) - 1)
+// with k = kld_grad_scale = kld_weight / B (times the upstream gradient): the KL term's backward (vae_nets.py:57-58) folded in.
+// Thread = one float4 of one row: all loads and stores are 16 bytes except the 33-stride d_z row (scalar, L1-resident).
 __global__ void latent_bwd_kernel(int B, const float* __restrict__ ml, const float* __restrict__ eps,
                                   const float* __restrict__ dzc, const float* __restrict__ dmu_ext,
-                                  const float* __restrict__ dlv_ext, float* __restrict__ dml) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * 32) return;
-    const int b = i >> 5, d = i & 31;
-    const float dz = dzc[b * 33 + d];
-    const float std_ = expf(0.5f * ml[b * 64 + 32 + d]);
-    dml[b * 64 + d] = dz + (dmu_ext ? dmu_ext[i] : 0.f);
-    dml[b * 64 + 32 + d] = dz * eps[i] * 0.5f * std_ + (dlv_ext ? dlv_ext[i] : 0.f);
+                                  const float* __restrict__ dlv_ext, float kld_grad_scale, float* __restrict__ dml) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * 8) return;
+    const long long b = i >> 3;
+    const int d4 = (int)(i & 7);
+    const float4* mrow = reinterpret_cast<const float4*>(ml + b * 64);
+    const float4 mu = __ldg(mrow + d4), lv = __ldg(mrow + 8 + d4);
+    const float4 e = __ldg(reinterpret_cast<const float4*>(eps + b * 32) + d4);
+    const float* dzr = dzc + b * 33 + d4 * 4;
+    const float dz[4] = {__ldg(dzr), __ldg(dzr + 1), __ldg(dzr + 2), __ldg(dzr + 3)};
+    float4 gm = make_float4(0.f, 0.f, 0.f, 0.f), gl = gm;
+    if (dmu_ext) gm = __ldg(reinterpret_cast<const float4*>(dmu_ext + b * 32) + d4);
+    if (dlv_ext) gl = __ldg(reinterpret_cast<const float4*>(dlv_ext + b * 32) + d4);
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, lvv[4] = {lv.x, lv.y, lv.z, lv.w}, ev[4] = {e.x, e.y, e.z, e.w};
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, glv[4] = {gl.x, gl.y, gl.z, gl.w};
+    float om[4], ol[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float std_ = expf(0.5f * lvv[j]);
+        om[j] = dz[j] + gmv[j];
+        ol[j] = dz[j] * ev[j] * 0.5f * std_ + glv[j];
+        if (kld_grad_scale != 0.f) {
+            om[j] += kld_grad_scale * muv[j];
+            ol[j] += kld_grad_scale * 0.5f * (expf(lvv[j]) - 1.f);
+        }
+    }
+    float4* orow = reinterpret_cast<float4*>(dml + b * 64);
+    orow[d4] = make_float4(om[0], om[1], om[2], om[3]);
+    orow[8 + d4] = make_float4(ol[0], ol[1], ol[2], ol[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -327,19 +393,25 @@ extern "C" int cvae_bn_pool_act_bwd(int batch, int height, int width, int channe
     return CVAE_OK;
 }
 
+extern "C" int cvae_latent_kld_partials(int batch) { return batch > 0 ? (batch + kLatRows - 1) / kLatRows : 0; }
+
 extern "C" int cvae_latent_fwd(int batch, int sample, const float* mu_logvar, const float* eps,
-                               const float* pred, float* z_pred, void* stream) {
+                               const float* pred, float* z_pred, double* kld_partial, void* stream) {
     CVAE_REQUIRE(batch > 0 && mu_logvar && pred && z_pred && (!sample || eps), CVAE_EINVAL, "latent_fwd: bad argument");
-    latent_fwd_kernel<<<(batch * 33 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(batch, sample, mu_logvar, eps, pred, z_pred);
+    CVAE_REQUIRE(((uintptr_t)mu_logvar | (uintptr_t)eps | (uintptr_t)z_pred) % 16 == 0, CVAE_EINVAL, "latent_fwd: tensors must be 16-byte aligned");
+    latent_fwd_kernel<<<cvae_latent_kld_partials(batch), 256, 0, (cudaStream_t)stream>>>(batch, sample, mu_logvar, eps, pred, z_pred, kld_partial);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
 
 extern "C" int cvae_latent_bwd(int batch, const float* mu_logvar, const float* eps, const float* d_z_pred,
-                               const float* dmu_ext, const float* dlogvar_ext, float* d_mu_logvar, void* stream) {
+                               const float* dmu_ext, const float* dlogvar_ext, float kld_grad_scale, float* d_mu_logvar, void* stream) {
     CVAE_REQUIRE(batch > 0 && mu_logvar && eps && d_z_pred && d_mu_logvar, CVAE_EINVAL, "latent_bwd: bad argument");
-    latent_bwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(batch, mu_logvar, eps, d_z_pred, dmu_ext,
-                                                                                 dlogvar_ext, d_mu_logvar);
+    CVAE_REQUIRE(((uintptr_t)mu_logvar | (uintptr_t)eps | (uintptr_t)dmu_ext | (uintptr_t)dlogvar_ext | (uintptr_t)d_mu_logvar) % 16 == 0, CVAE_EINVAL,
+                 "latent_bwd: tensors must be 16-byte aligned");
+    const long long items = (long long)batch * 8;
+    latent_bwd_kernel<<<(int)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(batch, mu_logvar, eps, d_z_pred, dmu_ext, dlogvar_ext,
+                                                                                   kld_grad_scale, d_mu_logvar);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }

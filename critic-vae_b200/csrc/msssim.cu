@@ -274,14 +274,20 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
 #undef CVAE_MS_FOR_TASKS
 
 // one block: KLD reduction + loss scalars + chain-rule coefficients
-__global__ void loss_finalize_kernel(int B, const float* __restrict__ ml, const double* __restrict__ sums,
-                                     float kld_weight, float* __restrict__ losses, float* __restrict__ coef) {
+__global__ void loss_finalize_kernel(int B, const float* __restrict__ ml, const double* __restrict__ kld_partial, int n_partial,
+                                     const double* __restrict__ sums, float kld_weight, float* __restrict__ losses,
+                                     float* __restrict__ coef) {
     __shared__ double red[32];
     double acc = 0.0;
-    for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
-        const int b = i >> 5, d = i & 31;
-        const float mu = ml[b * 64 + d], lv = ml[b * 64 + 32 + d];
-        acc += (double)(1.f + lv - mu * mu - expf(lv));
+    if (kld_partial) {   // the latent kernel already reduced the KL term per 64 rows: add the partials in block order
+        if (threadIdx.x == 0)
+            for (int i = 0; i < n_partial; ++i) acc += kld_partial[i];
+    } else {
+        for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
+            const int b = i >> 5, d = i & 31;
+            const float mu = ml[b * 64 + d], lv = ml[b * 64 + 32 + d];
+            acc += (double)(1.f + lv - mu * mu - expf(lv));
+        }
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -326,11 +332,11 @@ static size_t ms_smem(bool bwd) {
     return sizeof(float) * (size_t)(2 * kPyr + 5 * kPyr + (bwd ? 3 * kPyr : 0));
 }
 
-extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar,
+extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar, const double* kld_partial,
                              const float* window11, float kld_weight, double* sums, float* coef, float* losses,
                              void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    CVAE_REQUIRE(batch > 0 && recon && x && mu_logvar && window11 && sums && coef && losses, CVAE_EINVAL, "loss_fwd: bad argument");
+    CVAE_REQUIRE(batch > 0 && recon && x && (mu_logvar || kld_partial) && window11 && sums && coef && losses, CVAE_EINVAL, "loss_fwd: bad argument");
     Window w;
     memcpy(w.g, window11, sizeof(w.g));
     CVAE_OPT_IN_SMEM(msssim_kernel<false>, ms_smem(false));
@@ -339,7 +345,7 @@ extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, cons
     const int grid = planes < sm_count() ? planes : sm_count();
     msssim_kernel<false><<<grid, kMsThreads, ms_smem(false), stream>>>(planes, recon, x, w, sums, nullptr, nullptr, nullptr);
     CVAE_LAUNCH_CHECK();
-    loss_finalize_kernel<<<1, 1024, 0, stream>>>(batch, mu_logvar, sums, kld_weight, losses, coef);
+    loss_finalize_kernel<<<1, kld_partial ? 32 : 1024, 0, stream>>>(batch, mu_logvar, kld_partial, (batch + 63) / 64, sums, kld_weight, losses, coef);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -348,8 +354,8 @@ extern "C" int cvae_loss_bwd(int batch, const float* recon, const float* x, cons
                              const float* window11, float kld_weight, const float* coef, const float* grad_out,
                              float* d_recon, float* d_mu, float* d_logvar, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    CVAE_REQUIRE(batch > 0 && recon && x && mu_logvar && window11 && coef && d_recon && d_mu && d_logvar, CVAE_EINVAL,
-                 "loss_bwd: bad argument");
+    CVAE_REQUIRE(batch > 0 && recon && x && window11 && coef && d_recon && (d_mu == nullptr) == (d_logvar == nullptr) &&
+                     (d_mu == nullptr || mu_logvar), CVAE_EINVAL, "loss_bwd: bad argument");
     Window w;
     memcpy(w.g, window11, sizeof(w.g));
     CVAE_OPT_IN_SMEM(msssim_kernel<true>, ms_smem(true));
@@ -357,7 +363,9 @@ extern "C" int cvae_loss_bwd(int batch, const float* recon, const float* x, cons
     const int grid = planes < sm_count() ? planes : sm_count();
     msssim_kernel<true><<<grid, kMsThreads, ms_smem(true), stream>>>(planes, recon, x, w, nullptr, coef, grad_out, d_recon);
     CVAE_LAUNCH_CHECK();
-    kld_bwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, stream>>>(batch, mu_logvar, kld_weight, grad_out, d_mu, d_logvar);
-    CVAE_LAUNCH_CHECK();
+    if (d_mu) {   // NULL, NULL: the caller folds the KL term's backward into cvae_latent_bwd (kld_grad_scale)
+        kld_bwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, stream>>>(batch, mu_logvar, kld_weight, grad_out, d_mu, d_logvar);
+        CVAE_LAUNCH_CHECK();
+    }
     return CVAE_OK;
 }

@@ -65,8 +65,16 @@ __device__ float pack_value(const cvae_pack_job& j, long long i, bool& is_bf16) 
         return W[((size_t)n * 3 + c) * 25 + ky * 5 + kx];
     }
     const int cpt = j.k_channels / 16;  // K steps per tap
-    const int tap = ks / cpt, c = (ks % cpt) * 16 + k16;
-    switch (j.kind) {
+    int tap, c;
+    if (j.kind & CVAE_PACK_KORDER_BLOCK64) {   // (64-channel block, tap, 16-channel group): conv_wa.cu streams one block's taps back to back
+        const int taps = j.ksteps / cpt, blk = ks / (taps * 4), rem = ks - blk * taps * 4;
+        tap = rem >> 2;
+        c = blk * 64 + (rem & 3) * 16 + k16;
+    } else {
+        tap = ks / cpt;
+        c = (ks % cpt) * 16 + k16;
+    }
+    switch (j.kind & 0xFF) {
         case CVAE_PACK_FWD5:     // n = co, c = ci
             return W[((size_t)n * j.cin + c) * 25 + tap];
         case CVAE_PACK_DGRAD5:   // n = ci, c = co, flipped taps
@@ -122,6 +130,9 @@ extern "C" int cvae_pack_weights(const cvae_pack_job* jobs, int count, void* str
         CVAE_REQUIRE(jobs[i].src && jobs[i].dst, CVAE_EINVAL, "pack_weights: job %d has a null tensor", i);
         if (jobs[i].kind != CVAE_PACK_FC && jobs[i].kind != CVAE_PACK_DECIN)
             CVAE_REQUIRE(jobs[i].n % 16 == 0 && jobs[i].ksteps > 0, CVAE_EINVAL, "pack_weights: job %d shape", i);
+        if (jobs[i].kind & CVAE_PACK_KORDER_BLOCK64)
+            CVAE_REQUIRE(jobs[i].k_channels % 64 == 0 && (jobs[i].kind & 0xFF) != CVAE_PACK_PAIR8 && (jobs[i].kind & 0xFF) <= CVAE_PACK_PHASE_DGRAD &&
+                             jobs[i].n % 128 == 0, CVAE_EINVAL, "pack_weights: job %d cannot be packed block-major", i);
         pj.job[i] = jobs[i];
         pj.start[i] = total;
         total += cvae_pack_elems(&jobs[i]);

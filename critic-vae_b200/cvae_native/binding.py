@@ -51,6 +51,10 @@ lib.cvae_conv_debug_counters.argtypes = [c_void_p]
 lib.cvae_conv_debug_counters.restype = None
 lib.cvae_wgrad_debug_counters.argtypes = [c_void_p]
 lib.cvae_wgrad_debug_counters.restype = None
+lib.cvae_conv_wa_debug_counters.argtypes = [c_void_p]
+lib.cvae_conv_wa_debug_counters.restype = None
+lib.cvae_conv_wa_tune.argtypes = [c_int, c_int, c_int, c_int]
+lib.cvae_conv_wa_tune.restype = None
 lib.cvae_conv_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(WgradDesc)]
 lib.cvae_conv_wgrad_workspace_bytes.restype = c_i64
 lib.cvae_conv_wgrad.argtypes = [ctypes.POINTER(WgradDesc), c_void_p]
@@ -74,9 +78,10 @@ _SIGS = {
     "cvae_fc_bwd": ([c_int, P, P, P, P, P, P, P, P, P], c_int),
     "cvae_decin_fwd": ([c_int, P, P, P, P], c_int),
     "cvae_decin_bwd": ([c_int, P, P, P, P, P, P, P], c_int),
-    "cvae_latent_fwd": ([c_int, c_int, P, P, P, P, P], c_int),
-    "cvae_latent_bwd": ([c_int, P, P, P, P, P, P, P], c_int),
-    "cvae_loss_fwd": ([c_int, P, P, P, ctypes.POINTER(c_float), c_float, P, P, P, P], c_int),
+    "cvae_latent_kld_partials": ([c_int], c_int),
+    "cvae_latent_fwd": ([c_int, c_int, P, P, P, P, P, P], c_int),
+    "cvae_latent_bwd": ([c_int, P, P, P, P, P, c_float, P, P], c_int),
+    "cvae_loss_fwd": ([c_int, P, P, P, P, ctypes.POINTER(c_float), c_float, P, P, P, P], c_int),
     "cvae_loss_bwd": ([c_int, P, P, P, ctypes.POINTER(c_float), c_float, P, P, P, P, P, P], c_int),
     "cvae_adam_step": ([c_i64, P, P, P, P, P, c_float, c_float, c_float, c_float, c_float, P], c_int),
     "cvae_critic_param_count": ([], c_int),
@@ -92,7 +97,8 @@ for _name, (_args, _res) in _SIGS.items():
     getattr(lib, _name).restype = _res
 
 EXPORTS = ["cvae_last_error", "cvae_version", "cvae_check_device_fault", "cvae_conv_gemm", "cvae_conv_ksteps",
-           "cvae_conv_wgrad_workspace_bytes", "cvae_conv_wgrad", "cvae_conv_debug_counters", "cvae_wgrad_debug_counters"] + list(_SIGS)
+           "cvae_conv_wgrad_workspace_bytes", "cvae_conv_wgrad", "cvae_conv_debug_counters", "cvae_wgrad_debug_counters",
+           "cvae_conv_wa_debug_counters", "cvae_conv_wa_tune"] + list(_SIGS)
 
 
 def check(rc: int) -> None:
@@ -108,7 +114,8 @@ def stream_ptr():
 # enums of include/cvae.h
 LOAD_NHWC, LOAD_NCHW3, LOAD_S2D, LOAD_S2D_NCHW3_DTANH = 0, 1, 2, 3
 EPI_STATS, EPI_BIAS_RELU, EPI_PHASE_BIAS_RELU, EPI_PHASE_BIAS_TANH, EPI_MASK, EPI_PLAIN = 0, 1, 2, 3, 4, 5
-KTAB_GENERIC, KTAB_PAIR8 = 0, 1
+KTAB_GENERIC, KTAB_PAIR8, KTAB_BLOCK64 = 0, 1, 2
+PACK_KORDER_BLOCK64 = 0x100
 WGRAD_5X5, WGRAD_PHASE, WGRAD_SHIFT_FRAMES, WGRAD_SHIFT_PHASE12 = 0, 1, 2, 3
 PACK_FWD5, PACK_DGRAD5, PACK_PAIR8, PACK_PHASE_FWD, PACK_PHASE_DGRAD, PACK_FC, PACK_DECIN = range(7)
 ACT_RELU, ACT_TANH = 0, 1

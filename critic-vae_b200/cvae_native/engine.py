@@ -65,6 +65,7 @@ class Workspace:
             self.am = [e(B, h // 2, h // 2, co // 8, dtype=torch.int16) for (_, co, h) in ENC]
         self.ml = e(B, 64, dtype=f32)
         self.zc = e(B, 33, dtype=f32)
+        self.kld_partial = torch.zeros((B + 63) // 64, dtype=f64, device=dev)   # per-64-row KL sums from the latent kernel
         self.h0 = e(B, 4, 4, 256)
         self.d = [e(B, 4, 4, 128), e(B, 8, 8, 64), e(B, 16, 16, 32), e(B, 32, 32, 32)]
         self.recon = e(B, 3, 64, 64, dtype=f32)
@@ -125,7 +126,15 @@ class VAEEngine:
         dev = self.device
         jobs, self.packed = [], {}
 
+        # Layers whose GEMM has >= 128 output columns and a source in multiples of 64 channels run the weights-as-A
+        # kernel (csrc/conv_wa.cu, CVAE_KTAB_BLOCK64); it wants its K steps packed block-major.  CVAE_NO_WA=1 keeps
+        # every layer on the pixels-as-M kernel (A/B comparisons).
+        self.wa_keys = set() if os.environ.get("CVAE_NO_WA") else {"E2f", "E3f", "D0f", "D1f", "D2f", "E3g", "D0g", "D1g"}
+
         def add(key, kind, n, ksteps, kch, cout, cin, src, src2=None, dtype=torch.bfloat16, elems=None):
+            if key in self.wa_keys:
+                assert kch % 64 == 0 and n % 128 == 0, key
+                kind |= L.PACK_KORDER_BLOCK64
             numel = elems if elems is not None else n * ksteps * 16
             dst = torch.zeros(numel, dtype=dtype, device=dev)
             self.packed[key] = dst
@@ -197,6 +206,9 @@ class VAEEngine:
         b.record()
         self.profile.append((family, a, b))
 
+    def _ktab(self, key):
+        return L.KTAB_BLOCK64 if key in self.wa_keys else L.KTAB_GENERIC
+
     def _conv(self, **kw):
         d = L.ConvDesc(**{k: (_ptr(v) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
         self._timed("conv_gemm", lambda: L.check(L.lib.cvae_conv_gemm(ctypes.byref(d), L.stream_ptr())))
@@ -217,7 +229,7 @@ class VAEEngine:
                            epilogue=L.EPI_STATS, ktab=L.KTAB_PAIR8, src=x, wpack=self.packed["E0f"], out=ws.c[0], stats=stats)
             else:
                 self._conv(batch=B, height=h, width=h, ksize=5, src_channels=ci, n_total=co, loader=L.LOAD_NHWC,
-                           epilogue=L.EPI_STATS, ktab=L.KTAB_GENERIC, src=ws.a[i - 1], wpack=self.packed[f"E{i}f"],
+                           epilogue=L.EPI_STATS, ktab=self._ktab(f"E{i}f"), src=ws.a[i - 1], wpack=self.packed[f"E{i}f"],
                            out=ws.c[i], stats=stats)
             cname, bname = f"encoder.model.{ENC_CONV_IDX[i]}", f"encoder.model.{ENC_BN_IDX[i]}"
             L.check(L.lib.cvae_bn_finalize(co, B * h * h, int(training), _ptr(stats), _ptr(self.view(bname + ".weight")),
@@ -237,15 +249,17 @@ class VAEEngine:
         B, s = ws.B, L.stream_ptr()
         if pack:
             self.pack()
-        L.check(L.lib.cvae_latent_fwd(B, int(sample), _ptr(ws.ml), _ptr(eps), _ptr(pred), _ptr(ws.zc), s))
+        # fused reparametrise + critic concat + KL partial sums (consumed by loss_forward when it is given ws.ml itself)
+        L.check(L.lib.cvae_latent_fwd(B, int(sample), _ptr(ws.ml), _ptr(eps), _ptr(pred), _ptr(ws.zc),
+                                      _ptr(ws.kld_partial) if sample else None, s))
         L.check(L.lib.cvae_decin_fwd(B, _ptr(ws.zc), _ptr(self.packed["decin"]), _ptr(ws.h0), s))
         bias = lambda i: self.view(f"decoder.model.{DEC_CONV_IDX[i]}.bias")
         self._conv(batch=B, height=4, width=4, ksize=5, src_channels=256, n_total=128, loader=L.LOAD_NHWC,
-                   epilogue=L.EPI_BIAS_RELU, ktab=L.KTAB_GENERIC, src=ws.h0, wpack=self.packed["D0f"], out=ws.d[0], bias=bias(0))
+                   epilogue=L.EPI_BIAS_RELU, ktab=self._ktab("D0f"), src=ws.h0, wpack=self.packed["D0f"], out=ws.d[0], bias=bias(0))
         for i in (1, 2, 3):
             ci, co, h = DEC[i]
             self._conv(batch=B, height=h, width=h, ksize=3, src_channels=ci, n_total=4 * co, loader=L.LOAD_NHWC,
-                       epilogue=L.EPI_PHASE_BIAS_RELU, ktab=L.KTAB_GENERIC, src=ws.d[i - 1], wpack=self.packed[f"D{i}f"],
+                       epilogue=L.EPI_PHASE_BIAS_RELU, ktab=self._ktab(f"D{i}f"), src=ws.d[i - 1], wpack=self.packed[f"D{i}f"],
                        out=ws.d[i], bias=bias(i))
         self._conv(batch=B, height=32, width=32, ksize=3, src_channels=32, n_total=16, loader=L.LOAD_NHWC,
                    epilogue=L.EPI_PHASE_BIAS_TANH, ktab=L.KTAB_GENERIC, src=ws.d[3], wpack=self.packed["D4f"],
@@ -253,14 +267,19 @@ class VAEEngine:
         return ws.recon
 
     # ---- loss ---------------------------------------------------------------------------------
-    def loss_forward(self, recon, x, ml, ws, kld_weight=KLD_WEIGHT):
-        L.check(L.lib.cvae_loss_fwd(ws.B, _ptr(recon), _ptr(x), _ptr(ml), self.window, kld_weight, _ptr(ws.loss_sums),
-                                    _ptr(ws.coef), _ptr(ws.losses), L.stream_ptr()))
+    def loss_forward(self, recon, x, ml, ws, kld_weight=KLD_WEIGHT, fused_kld=False):
+        """`fused_kld`: ml is ws.ml of the decode() that just ran with sample=True, so the KL partial sums the latent
+        kernel left in ws.kld_partial are used instead of re-reading mu / logvar (TrainStep)."""
+        L.check(L.lib.cvae_loss_fwd(ws.B, _ptr(recon), _ptr(x), _ptr(ml), _ptr(ws.kld_partial) if fused_kld else None, self.window,
+                                    kld_weight, _ptr(ws.loss_sums), _ptr(ws.coef), _ptr(ws.losses), L.stream_ptr()))
         return ws.losses
 
-    def loss_backward(self, recon, x, ml, ws, grad_out=None, kld_weight=KLD_WEIGHT):
+    def loss_backward(self, recon, x, ml, ws, grad_out=None, kld_weight=KLD_WEIGHT, fused_kld=False):
+        """`fused_kld`: skip the KL term's backward here; backward(..., kld_grad_scale=kld_weight / B) adds it inside the
+        latent backward kernel (only valid with grad_out None, i.e. an upstream gradient of 1)."""
         L.check(L.lib.cvae_loss_bwd(ws.B, _ptr(recon), _ptr(x), _ptr(ml), self.window, kld_weight, _ptr(ws.coef),
-                                    _ptr(grad_out), _ptr(ws.d_recon), _ptr(ws.d_mu), _ptr(ws.d_lv), L.stream_ptr()))
+                                    _ptr(grad_out), _ptr(ws.d_recon), None if fused_kld else _ptr(ws.d_mu),
+                                    None if fused_kld else _ptr(ws.d_lv), L.stream_ptr()))
         return ws.d_recon, ws.d_mu, ws.d_lv
 
     # ---- backward -----------------------------------------------------------------------------
@@ -302,7 +321,7 @@ class VAEEngine:
             launch(L.stream_ptr())
         self._side_used = True
 
-    def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None):
+    def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None, kld_grad_scale=0.0):
         """Gradients of every parameter into the flat buffer `g` (default self.gflat), given the
         gradients of the loss w.r.t. recon / mu / logvar.  Mirrors autograd through vae_nets.py:14-19."""
         g = self.gflat if g is None else g
@@ -324,16 +343,17 @@ class VAEEngine:
             self._wgrad(g, f"{dm}{DEC_CONV_IDX[i]}", kind=L.WGRAD_PHASE, batch=B, height=h, width=h, cout=co, cin=ci,
                         x=ws.d[i - 1], dy=ws.g_d[i])
             self._conv(batch=B, height=h, width=h, ksize=3, src_channels=4 * co, n_total=ci, loader=L.LOAD_S2D,
-                       epilogue=L.EPI_MASK, ktab=L.KTAB_GENERIC, src=ws.g_d[i], wpack=self.packed[f"D{i}g"],
+                       epilogue=L.EPI_MASK, ktab=self._ktab(f"D{i}g"), src=ws.g_d[i], wpack=self.packed[f"D{i}g"],
                        out=ws.g_d[i - 1], act=ws.d[i - 1])
         self._wgrad(g, dm + "0", kind=L.WGRAD_5X5, batch=B, height=4, width=4, cout=128, cin=256, x=ws.h0, dy=ws.g_d[0])
         self._conv(batch=B, height=4, width=4, ksize=5, src_channels=128, n_total=256, loader=L.LOAD_NHWC,
-                   epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_d[0], wpack=self.packed["D0g"], out=ws.g_h0)
+                   epilogue=L.EPI_PLAIN, ktab=self._ktab("D0g"), src=ws.g_d[0], wpack=self.packed["D0g"], out=ws.g_h0)
         self._leaf(lambda st: L.check(L.lib.cvae_decin_bwd(B, _ptr(ws.g_h0), _ptr(ws.zc), None, None,
                                                            _ptr(G("decoder.decoder_input.weight")),
                                                            _ptr(G("decoder.decoder_input.bias")), st)))
         L.check(L.lib.cvae_decin_bwd(B, _ptr(ws.g_h0), None, _ptr(self.packed["decin"]), _ptr(ws.dzc), None, None, s))
-        L.check(L.lib.cvae_latent_bwd(B, _ptr(ws.ml), _ptr(eps), _ptr(ws.dzc), _ptr(d_mu), _ptr(d_lv), _ptr(ws.dml), s))
+        L.check(L.lib.cvae_latent_bwd(B, _ptr(ws.ml), _ptr(eps), _ptr(ws.dzc), _ptr(d_mu), _ptr(d_lv), float(kld_grad_scale),
+                                      _ptr(ws.dml), s))
         self._leaf(lambda st: L.check(L.lib.cvae_fc_bwd(B, _ptr(ws.dml), _ptr(ws.a[3]), None, None,
                                                         _ptr(G("encoder.fc_mu.weight")), _ptr(G("encoder.fc_var.weight")),
                                                         _ptr(G("encoder.fc_mu.bias")), _ptr(G("encoder.fc_var.bias")), st)))
@@ -351,7 +371,7 @@ class VAEEngine:
             else:
                 self._wgrad(g, cname, kind=L.WGRAD_5X5, batch=B, height=h, width=h, cout=co, cin=ci, x=ws.a[i - 1], dy=ws.g_c[i])
                 self._conv(batch=B, height=h, width=h, ksize=5, src_channels=co, n_total=ci, loader=L.LOAD_NHWC,
-                           epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
+                           epilogue=L.EPI_PLAIN, ktab=self._ktab(f"E{i}g"), src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
         if self._side_used:
             torch.cuda.current_stream().wait_stream(self.side_stream)
         if self._fold_used:

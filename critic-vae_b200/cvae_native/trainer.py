@@ -18,7 +18,7 @@ import os
 import torch
 
 from . import binding as L
-from .engine import VAEEngine
+from .engine import VAEEngine, KLD_WEIGHT
 
 
 def shard_batch(idx, rank, world):
@@ -75,9 +75,10 @@ class TrainStep:
         if joined is not None:
             torch.cuda.current_stream().wait_event(joined)
         eng.decode(self.pred, self.eps, True, ws)
-        eng.loss_forward(ws.recon, self.x, ws.ml, ws)
-        eng.loss_backward(ws.recon, self.x, ws.ml, ws)
-        eng.backward(self.x, self.eps, ws, ws.d_recon, ws.d_mu, ws.d_lv)
+        # the KL term rides along with the latent kernels: partial sums in the forward, its gradient in the backward
+        eng.loss_forward(ws.recon, self.x, ws.ml, ws, fused_kld=True)
+        eng.loss_backward(ws.recon, self.x, ws.ml, ws, fused_kld=True)
+        eng.backward(self.x, self.eps, ws, ws.d_recon, None, None, kld_grad_scale=KLD_WEIGHT / self.B)
 
     def _back(self):
         self.eng.adam_step(self.lr, grad_scale=1.0 / self.world)

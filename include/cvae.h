@@ -54,7 +54,13 @@ enum cvae_epilogue {
     CVAE_EPI_MASK = 4,           /* * (act > 0), bf16 NHWC (ReLU backward)                           */
     CVAE_EPI_PLAIN = 5           /* bf16 NHWC                                                        */
 };
-enum cvae_ktab { CVAE_KTAB_GENERIC = 0, CVAE_KTAB_PAIR8 = 1 /* 8-channel source, two taps per K step */ };
+enum cvae_ktab {
+    CVAE_KTAB_GENERIC = 0,
+    CVAE_KTAB_PAIR8 = 1,   /* 8-channel source, two taps per K step */
+    CVAE_KTAB_BLOCK64 = 2  /* weights packed block-major (CVAE_PACK_KORDER_BLOCK64): run the weights-as-A kernel (conv_wa.cu):
+                              src_channels % 64 == 0, n_total % 128 == 0, loader NHWC (or S2D with 4 x 64 channels), any
+                              epilogue except PHASE_BIAS_TANH.  Same results as the GENERIC path. */
+};
 
 typedef struct {
     int32_t batch, height, width;
@@ -74,6 +80,11 @@ typedef struct {
 } cvae_conv_desc;
 
 int cvae_conv_gemm(const cvae_conv_desc* d, void* stream);
+/* tuning / test hook for the weights-as-A kernel: force cluster size (1, 2, 4), grid size, (block, tap) units per
+ * weight stage and a minimum number of tiles per CTA; 0 = automatic.  Process-wide. */
+void cvae_conv_wa_tune(int cluster, int grid, int units_per_stage, int tiles_per_cta);
+/* profiling aid: device buffer of >= 8 * 148 uint64 cycle counters of the weights-as-A kernel's MMA thread (NULL = off) */
+void cvae_conv_wa_debug_counters(void* device_buf);
 /* profiling aid: device buffer of >= 8 * 148 uint64 cycle counters written by the pipelined kernel (NULL = off) */
 void cvae_conv_debug_counters(void* device_buf);
 /* number of K=16 steps of a conv GEMM: the packed weight tensor is [n_total/nb][ksteps][nb][16] bf16,
@@ -123,6 +134,9 @@ enum cvae_pack_kind {
     CVAE_PACK_FC = 5,          /* src = fc_mu.weight, src2 = fc_var.weight -> fp32 [4096 nhwc][64]    */
     CVAE_PACK_DECIN = 6        /* src = decoder_input.weight, src2 = bias -> fp32 [34][4096 nhwc]     */
 };
+/* OR-ed into `kind` of the conv forms: K steps ordered (64-channel block, tap, 16-channel group) instead of
+ * (tap, 16-channel group) -- the order the weights-as-A kernel (CVAE_KTAB_BLOCK64) streams; k_channels % 64 == 0 */
+#define CVAE_PACK_KORDER_BLOCK64 0x100
 typedef struct {
     int32_t kind, n, ksteps, k_channels, cout, cin;
     const void* src;
@@ -173,21 +187,31 @@ int cvae_decin_bwd(int batch, const void* d_out, const float* z_pred, const floa
 /* ------------------------------------------------------------------------------------------------
  * Latent: z = mu + eps * exp(0.5 logvar) (vae_nets.py:48-51; eps supplied by the host for parity,
  * sample = 0 decodes the mean as evaluate() does, :43-44) and the critic-value concat (:143):
- * z_pred fp32 [B][33] = z | pred.  Backward adds the loss's direct gradients on mu / logvar.
+ * z_pred fp32 [B][33] = z | pred.  The same pass reduces the KL term of vae_loss (vae_nets.py:57-58,
+ * sum(1 + logvar - mu^2 - exp(logvar))) into kld_partial: one double per 64 rows
+ * (cvae_latent_kld_partials(batch) of them; NULL = skip), which cvae_loss_fwd can take instead of
+ * re-reading mu / logvar.  Backward adds the loss's direct gradients on mu / logvar (dmu_ext /
+ * dlogvar_ext, may be NULL) and, when kld_grad_scale != 0, the KL term's own backward
+ * (kld_grad_scale = kld_weight / batch x upstream gradient).  All tensors 16-byte aligned.
  * ---------------------------------------------------------------------------------------------- */
+int cvae_latent_kld_partials(int batch);
 int cvae_latent_fwd(int batch, int sample, const float* mu_logvar, const float* eps, const float* pred,
-                    float* z_pred, void* stream);
+                    float* z_pred, double* kld_partial, void* stream);
 int cvae_latent_bwd(int batch, const float* mu_logvar, const float* eps, const float* d_z_pred,
-                    const float* dmu_ext, const float* dlogvar_ext, float* d_mu_logvar, void* stream);
+                    const float* dmu_ext, const float* dlogvar_ext, float kld_grad_scale, float* d_mu_logvar,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * vae_loss (vae_nets.py:53-62): MS-SSIM (vae_nets.py:150-247, including the upstream window sign)
  * + KLD * kld_weight.  recon, x: fp32 NCHW [B][3][64][64]; window11: HOST pointer to the 11
  * normalised 1-D window weights; sums: [10] double scratch; coef: [8] float scratch carried to the
  * backward; losses: [3] = total, recon, KLD.  grad_out: device scalar (NULL = 1).
+ * kld_partial: the per-64-row KL partial sums of cvae_latent_fwd for the same mu_logvar (NULL: the
+ * KL term is reduced from mu_logvar here).  cvae_loss_bwd: d_mu / d_logvar may both be NULL when the
+ * caller folds the KL backward into cvae_latent_bwd.
  * ---------------------------------------------------------------------------------------------- */
-int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar, const float* window11,
-                  float kld_weight, double* sums, float* coef, float* losses, void* stream);
+int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar, const double* kld_partial,
+                  const float* window11, float kld_weight, double* sums, float* coef, float* losses, void* stream);
 int cvae_loss_bwd(int batch, const float* recon, const float* x, const float* mu_logvar, const float* window11,
                   float kld_weight, const float* coef, const float* grad_out, float* d_recon, float* d_mu,
                   float* d_logvar, void* stream);

@@ -68,6 +68,14 @@ def pack_generic(Wg):
     return pack_kblocks(Wg.reshape(N, T * (C // 16), 16))
 
 
+def pack_block64(Wg):
+    """Wg [N][taps][C] (C % 64 == 0, N % 128 == 0) -> packed bf16 with K steps ordered (64-channel block, tap,
+    16-channel group): the order conv_wa.cu streams (CVAE_PACK_KORDER_BLOCK64)."""
+    N, T, C = Wg.shape
+    x = Wg.reshape(N, T, C // 64, 4, 16).permute(0, 2, 1, 3, 4).reshape(N, (C // 64) * T * 4, 16)
+    return pack_kblocks(x)
+
+
 def pack_pair8_e0(W):
     """Encoder conv 0: W [32][3][5][5]; 8-channel padded source, 13 K steps of two taps each
     (conv_gemm.cu PAIR8 table)."""

@@ -197,3 +197,130 @@ def test_dgrad_last_conv_from_nchw_grad():
              epilogue=L.EPI_MASK, ktab=L.KTAB_GENERIC, src=g.cuda(), src2=recon.cuda(),
              wpack=packref.pack_generic(rb(Wg)).cuda(), out=out, act=nhwc_bf16(act))
     np.testing.assert_allclose(from_nhwc(out).numpy(), rb(ref).numpy(), rtol=2 ** -7, atol=2e-3 * ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# weights-as-A kernel (csrc/conv_wa.cu, CVAE_KTAB_BLOCK64): same operations, block-major packed weights.
+# Every case runs with automatic tiling and with forced cluster sizes / grid sizes / tile counts, including
+# ragged ones (a grid that does not divide the rows, more tiles than rows).
+# ------------------------------------------------------------------------------------------------------------
+WA_TUNES = [(0, 0, 0, 0), (1, 0, 1, 0), (2, 0, 2, 2), (4, 0, 0, 0), (1, 3, 0, 3), (2, 6, 1, 0)]
+
+
+@pytest.fixture
+def wa_tune():
+    L = _native()
+    yield lambda t: L.lib.cvae_conv_wa_tune(*t)
+    L.lib.cvae_conv_wa_tune(0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("tune", WA_TUNES)
+@pytest.mark.parametrize("B,Cin,Cout,HW", [(5, 64, 128, 16), (7, 128, 256, 8), (50, 64, 128, 16)])
+def test_wa_encoder_conv_with_stats(B, Cin, Cout, HW, tune, wa_tune):
+    L = _native()
+    wa_tune(tune)
+    x, Wt = rb(_rand((B, Cin, HW, HW), 1)), rb(_rand((Cout, Cin, 5, 5), 2, 0.05))
+    ref = F.conv2d(x.double(), Wt.double(), padding=2).float()
+    wp = packref.pack_block64(packref.gemm_weights_fwd5(Wt)).cuda()
+    out = torch.zeros(B, HW, HW, Cout, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(2, Cout, dtype=torch.float64, device="cuda")
+    run_conv(L, B=B, H=HW, W=HW, ksize=5, src_channels=Cin, n_total=Cout, loader=L.LOAD_NHWC,
+             epilogue=L.EPI_STATS, ktab=L.KTAB_BLOCK64, src=nhwc_bf16(x), wpack=wp, out=out, stats=stats)
+    got = from_nhwc(out)
+    np.testing.assert_allclose(got.numpy(), rb(ref).numpy(), rtol=2 ** -7, atol=1e-3)
+    g64 = got.double()
+    np.testing.assert_allclose(stats[0].cpu().numpy(), g64.sum((0, 2, 3)).numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(stats[1].cpu().numpy(), (g64 * g64).sum((0, 2, 3)).numpy(), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("tune", WA_TUNES)
+def test_wa_decoder_conv0_bias_relu(tune, wa_tune):
+    L = _native()
+    wa_tune(tune)
+    B = 6
+    x, Wt, b = rb(_rand((B, 256, 4, 4), 5)), rb(_rand((128, 256, 5, 5), 6, 0.02)), _rand((128,), 7, 0.1)
+    ref = torch.relu(F.conv2d(x.double(), Wt.double(), b.double(), padding=2)).float()
+    out = torch.zeros(B, 4, 4, 128, dtype=torch.bfloat16, device="cuda")
+    run_conv(L, B=B, H=4, W=4, ksize=5, src_channels=256, n_total=128, loader=L.LOAD_NHWC,
+             epilogue=L.EPI_BIAS_RELU, ktab=L.KTAB_BLOCK64, src=nhwc_bf16(x),
+             wpack=packref.pack_block64(packref.gemm_weights_fwd5(Wt)).cuda(), out=out, bias=b.cuda())
+    np.testing.assert_allclose(from_nhwc(out).numpy(), rb(ref).numpy(), rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("tune", WA_TUNES[:4])
+@pytest.mark.parametrize("B,Cin,Cout,HW", [(3, 128, 64, 4), (3, 64, 32, 8), (33, 128, 64, 4)])
+def test_wa_decoder_upsample_folded_conv(B, Cin, Cout, HW, tune, wa_tune):
+    L = _native()
+    wa_tune(tune)
+    x, Wt, b = rb(_rand((B, Cin, HW, HW), 8)), _rand((Cout, Cin, 5, 5), 9, 0.05), _rand((Cout,), 10, 0.1)
+    Wg = packref.gemm_weights_phase_fwd(Wt)
+    Weff = rb(Wg).reshape(2, 2, Cout, 3, 3, Cin)
+    ref = torch.zeros(B, Cout, 2 * HW, 2 * HW, dtype=torch.float64)
+    for a in (0, 1):
+        for bb in (0, 1):
+            ref[:, :, a::2, bb::2] = F.conv2d(x.double(), Weff[a, bb].permute(0, 3, 1, 2).double(), b.double(), padding=1)
+    ref = torch.relu(ref).float()
+    out = torch.zeros(B, 2 * HW, 2 * HW, Cout, dtype=torch.bfloat16, device="cuda")
+    run_conv(L, B=B, H=HW, W=HW, ksize=3, src_channels=Cin, n_total=4 * Cout, loader=L.LOAD_NHWC,
+             epilogue=L.EPI_PHASE_BIAS_RELU, ktab=L.KTAB_BLOCK64, src=nhwc_bf16(x),
+             wpack=packref.pack_block64(Wg).cuda(), out=out, bias=b.cuda())
+    np.testing.assert_allclose(from_nhwc(out).numpy(), rb(ref).numpy(), rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("tune", WA_TUNES[:4])
+@pytest.mark.parametrize("B,Cin,Cout,HW", [(4, 128, 256, 8), (5, 256, 128, 4), (40, 128, 256, 8)])
+def test_wa_dgrad_5x5(B, Cin, Cout, HW, tune, wa_tune):
+    L = _native()
+    wa_tune(tune)
+    dy, Wt = rb(_rand((B, Cout, HW, HW), 14)), rb(_rand((Cout, Cin, 5, 5), 15, 0.05))
+    ref = F.conv_transpose2d(dy.double(), Wt.double(), padding=2).float()
+    out = torch.zeros(B, HW, HW, Cin, dtype=torch.bfloat16, device="cuda")
+    run_conv(L, B=B, H=HW, W=HW, ksize=5, src_channels=Cout, n_total=Cin, loader=L.LOAD_NHWC,
+             epilogue=L.EPI_PLAIN, ktab=L.KTAB_BLOCK64, src=nhwc_bf16(dy),
+             wpack=packref.pack_block64(packref.gemm_weights_dgrad5(Wt)).cuda(), out=out)
+    np.testing.assert_allclose(from_nhwc(out).numpy(), rb(ref).numpy(), rtol=2 ** -7, atol=2e-3 * ref.abs().max().item())
+
+
+@pytest.mark.parametrize("tune", WA_TUNES[:4])
+@pytest.mark.parametrize("B", [3, 21])
+def test_wa_dgrad_upsample_folded_with_relu_mask(B, tune, wa_tune):
+    """D1's data gradient: space-to-depth source with 4 x 64 channels (one TMA view per phase) + ReLU mask."""
+    L = _native()
+    wa_tune(tune)
+    Cin, Cout, HW = 128, 64, 4
+    act = rb(torch.relu(_rand((B, Cin, HW, HW), 16)))
+    dy, Wt = rb(_rand((B, Cout, 2 * HW, 2 * HW), 17)), _rand((Cout, Cin, 5, 5), 18, 0.05)
+    Wg = packref.gemm_weights_phase_dgrad(Wt)                       # [Cin][9][4Cout]
+    Weff = rb(packref.phase_weights(Wt)).reshape(2, 2, Cout, 3, 3, Cin)
+    xs = act.double().clone().requires_grad_(True)
+    ys = []
+    for a in (0, 1):
+        for bb in (0, 1):
+            ys.append((a, bb, F.conv2d(xs, Weff[a, bb].permute(0, 3, 1, 2).double(), padding=1)))
+    loss = sum((yy * dy.double()[:, :, a::2, bb::2]).sum() for a, bb, yy in ys)
+    loss.backward()
+    ref = (xs.grad * (act > 0)).float()
+    out = torch.zeros(B, HW, HW, Cin, dtype=torch.bfloat16, device="cuda")
+    run_conv(L, B=B, H=HW, W=HW, ksize=3, src_channels=4 * Cout, n_total=Cin, loader=L.LOAD_S2D,
+             epilogue=L.EPI_MASK, ktab=L.KTAB_BLOCK64, src=nhwc_bf16(dy),
+             wpack=packref.pack_block64(rb(Wg)).cuda(), out=out, act=nhwc_bf16(act))
+    np.testing.assert_allclose(from_nhwc(out).numpy(), rb(ref).numpy(), rtol=2 ** -7, atol=2e-3 * ref.abs().max().item())
+
+
+def test_wa_device_packing_matches_host_packing():
+    """cvae_pack_weights with CVAE_PACK_KORDER_BLOCK64 == tests/packref.pack_block64, bit for bit."""
+    L = _native()
+    W1 = _rand((256, 128, 5, 5), 30, 0.05)       # E3: forward n = 256, data gradient n = 128
+    W2 = _rand((64, 128, 5, 5), 31, 0.05)        # D1: phase forward n = 256, phase data gradient n = 128
+    cases = [(L.PACK_FWD5, W1, 256, 25 * 128 // 16, 128, packref.pack_block64(packref.gemm_weights_fwd5(W1))),
+             (L.PACK_DGRAD5, W1, 128, 25 * 256 // 16, 256, packref.pack_block64(packref.gemm_weights_dgrad5(W1))),
+             (L.PACK_PHASE_FWD, W2, 256, 9 * 128 // 16, 128, packref.pack_block64(packref.gemm_weights_phase_fwd(W2))),
+             (L.PACK_PHASE_DGRAD, W2, 128, 9 * 256 // 16, 256, packref.pack_block64(packref.gemm_weights_phase_dgrad(W2)))]
+    for kind, W, n, ksteps, kch, ref in cases:
+        dst = torch.zeros(n * ksteps * 16, dtype=torch.bfloat16, device="cuda")
+        Wd = W.cuda()
+        job = L.PackJob(kind=kind | L.PACK_KORDER_BLOCK64, n=n, ksteps=ksteps, k_channels=kch, cout=W.shape[0], cin=W.shape[1],
+                        src=Wd.data_ptr(), src2=None, dst=dst.data_ptr())
+        L.check(L.lib.cvae_pack_weights((L.PackJob * 1)(job), 1, L.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(dst.cpu().view(torch.int16), ref.view(torch.int16)), kind

@@ -158,7 +158,7 @@ def test_linear_layers(B):
     h = F.linear(torch.cat((z, pred.double()), 1), W[4], W[5]).view(-1, 256, 4, 4)
     zc = torch.empty(B, 33, device="cuda")
     eps_d, pred_d = eps.cuda(), pred.cuda()      # keep device copies alive across the async launches
-    L.check(L.lib.cvae_latent_fwd(B, 1, ptr(ml), ptr(eps_d), ptr(pred_d), ptr(zc), L.stream_ptr()))
+    L.check(L.lib.cvae_latent_fwd(B, 1, ptr(ml), ptr(eps_d), ptr(pred_d), ptr(zc), None, L.stream_ptr()))
     h_dev = torch.empty(B, 4, 4, 256, dtype=torch.bfloat16, device="cuda")
     L.check(L.lib.cvae_decin_fwd(B, ptr(zc), ptr(wdec), ptr(h_dev), L.stream_ptr()))
     sync(L)
@@ -176,7 +176,7 @@ def test_linear_layers(B):
     dh_d, dmu_d, dlv_d = nhwc_bf16(dh), dmu_e.cuda(), dlv_e.cuda()
     L.check(L.lib.cvae_decin_bwd(B, ptr(dh_d), ptr(zc), ptr(wdec), ptr(dzc), ptr(dwd), ptr(dbd), L.stream_ptr()))
     dml = torch.empty(B, 64, device="cuda")
-    L.check(L.lib.cvae_latent_bwd(B, ptr(ml), ptr(eps_d), ptr(dzc), ptr(dmu_d), ptr(dlv_d), ptr(dml), L.stream_ptr()))
+    L.check(L.lib.cvae_latent_bwd(B, ptr(ml), ptr(eps_d), ptr(dzc), ptr(dmu_d), ptr(dlv_d), 0.0, ptr(dml), L.stream_ptr()))
     da = torch.empty(B, 4, 4, 256, dtype=torch.bfloat16, device="cuda")
     dwmu, dwvar = torch.empty(32, 4096, device="cuda"), torch.empty(32, 4096, device="cuda")
     dbmu, dbvar = torch.empty(32, device="cuda"), torch.empty(32, device="cuda")
@@ -208,7 +208,7 @@ def test_loss_forward_backward_vs_golden(golden_dir, tag, B):
     sums = torch.zeros(10, dtype=torch.float64, device="cuda")
     coef, losses = torch.zeros(8, device="cuda"), torch.zeros(3, device="cuda")
     rd, xd = r.cuda(), x.cuda()
-    L.check(L.lib.cvae_loss_fwd(B, ptr(rd), ptr(xd), ptr(ml), _window(), 0.001, ptr(sums), ptr(coef), ptr(losses), L.stream_ptr()))
+    L.check(L.lib.cvae_loss_fwd(B, ptr(rd), ptr(xd), ptr(ml), None, _window(), 0.001, ptr(sums), ptr(coef), ptr(losses), L.stream_ptr()))
     dr = torch.zeros_like(rd)
     dmu, dlv = torch.zeros(B, 32, device="cuda"), torch.zeros(B, 32, device="cuda")
     L.check(L.lib.cvae_loss_bwd(B, ptr(rd), ptr(xd), ptr(ml), _window(), 0.001, ptr(coef), None, ptr(dr), ptr(dmu), ptr(dlv), L.stream_ptr()))
@@ -241,9 +241,62 @@ def test_loss_nan_semantics():
     sums = torch.zeros(10, dtype=torch.float64, device="cuda")
     coef, losses = torch.zeros(8, device="cuda"), torch.zeros(3, device="cuda")
     rd, xd = r.cuda(), x.cuda()
-    L.check(L.lib.cvae_loss_fwd(B, ptr(rd), ptr(xd), ptr(ml), _window(), 0.001, ptr(sums), ptr(coef), ptr(losses), L.stream_ptr()))
+    L.check(L.lib.cvae_loss_fwd(B, ptr(rd), ptr(xd), ptr(ml), None, _window(), 0.001, ptr(sums), ptr(coef), ptr(losses), L.stream_ptr()))
     sync(L)
     assert torch.isnan(losses[0]) and torch.isnan(losses[1]) and losses[2].item() == 0.0
+
+
+@pytest.mark.parametrize("B", [1, 5, 64, 65, 200, 4099])
+def test_fused_latent_kld_kernels(B):
+    """The vectorised latent kernel: z | pred bit-identical to fma(eps, exp(0.5 logvar), mu) per element (the same
+    expression the scalar round-1 kernel evaluated), KL partial sums per 64 rows equal to the fp64 sum of the
+    per-element fp32 terms, loss_fwd fed with the partials == loss_fwd reducing mu / logvar itself, and the
+    backward with the KL term folded in == latent_bwd + kld_bwd (vae_nets.py:48-51,57-58,143)."""
+    L = _native()
+    g = torch.Generator().manual_seed(B)
+    ml = torch.randn(B, 64, generator=g)
+    eps, pred = torch.randn(B, 32, generator=g), torch.rand(B, generator=g)
+    ml_d, eps_d, pred_d = ml.cuda(), eps.cuda(), pred.cuda()
+    zc = torch.full((B, 33), float("nan"), device="cuda")
+    nparts = L.lib.cvae_latent_kld_partials(B)
+    assert nparts == (B + 63) // 64
+    parts = torch.full((nparts,), float("nan"), dtype=torch.float64, device="cuda")
+    L.check(L.lib.cvae_latent_fwd(B, 1, ptr(ml_d), ptr(eps_d), ptr(pred_d), ptr(zc), ptr(parts), L.stream_ptr()))
+    zc0 = torch.empty(B, 33, device="cuda")
+    L.check(L.lib.cvae_latent_fwd(B, 0, ptr(ml_d), None, ptr(pred_d), ptr(zc0), None, L.stream_ptr()))
+    sync(L)
+    # device expression on the device (torch's exp / fma differ from expf in the last bit, so compare to 2 ulp and
+    # pin the exact bits against a device-side evaluation of the same formula)
+    mu, lv = ml_d[:, :32], ml_d[:, 32:]
+    ref = torch.cat((torch.addcmul(mu, eps_d, torch.exp(0.5 * lv)), pred_d[:, None]), 1)
+    np.testing.assert_allclose(zc.cpu().numpy(), ref.cpu().numpy(), rtol=3e-7, atol=1e-7)
+    assert torch.equal(zc[:, 32], pred_d) and torch.equal(zc0[:, :32], mu) and torch.equal(zc0[:, 32], pred_d)
+    terms = (1.0 + lv - mu * mu - torch.exp(lv)).double().cpu()
+    want = torch.stack([terms[i * 64:(i + 1) * 64].sum() for i in range(nparts)])
+    np.testing.assert_allclose(parts.cpu().numpy(), want.numpy(), rtol=1e-6, atol=1e-4)
+    # loss_fwd with the partials == loss_fwd without
+    x = synth.make_frames(min(B, 4), seed=61)
+    if B <= 4:
+        r = (x * 0.9 + 0.05).contiguous()
+        sums = torch.zeros(10, dtype=torch.float64, device="cuda")
+        coef, l0, l1 = torch.zeros(8, device="cuda"), torch.zeros(3, device="cuda"), torch.zeros(3, device="cuda")
+        rd, xd = r.cuda(), x.cuda()
+        L.check(L.lib.cvae_loss_fwd(B, ptr(rd), ptr(xd), ptr(ml_d), None, _window(), 0.001, ptr(sums), ptr(coef), ptr(l0), L.stream_ptr()))
+        L.check(L.lib.cvae_loss_fwd(B, ptr(rd), ptr(xd), None, ptr(parts), _window(), 0.001, ptr(sums), ptr(coef), ptr(l1), L.stream_ptr()))
+        sync(L)
+        np.testing.assert_allclose(l1.cpu().numpy(), l0.cpu().numpy(), rtol=1e-6)
+    # backward: folded KL term == separate kld_bwd + latent_bwd
+    dzc = torch.randn(B, 33, generator=g).cuda()
+    k = 0.001 / B
+    dmu, dlv = k * mu, k * 0.5 * (torch.exp(lv) - 1.0)
+    d_sep, d_fused = torch.empty(B, 64, device="cuda"), torch.empty(B, 64, device="cuda")
+    L.check(L.lib.cvae_latent_bwd(B, ptr(ml_d), ptr(eps_d), ptr(dzc), ptr(dmu.contiguous()), ptr(dlv.contiguous()), 0.0, ptr(d_sep), L.stream_ptr()))
+    L.check(L.lib.cvae_latent_bwd(B, ptr(ml_d), ptr(eps_d), ptr(dzc), None, None, k, ptr(d_fused), L.stream_ptr()))
+    sync(L)
+    want_mu = dzc[:, :32] + dmu
+    want_lv = dzc[:, :32] * eps_d * 0.5 * torch.exp(0.5 * lv) + dlv
+    np.testing.assert_allclose(d_sep.cpu().numpy(), torch.cat((want_mu, want_lv), 1).cpu().numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(d_fused.cpu().numpy(), d_sep.cpu().numpy(), rtol=2e-6, atol=1e-7)
 
 
 def test_adam_matches_torch():

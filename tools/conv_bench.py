@@ -11,6 +11,8 @@ from cvae_native import binding as L
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 B = int(args[0]) if args else 256
 SWEEP = "--sweep" in sys.argv
+WA = "--wa" in sys.argv          # run the layers the weights-as-A kernel covers through it (CVAE_KTAB_BLOCK64)
+WA_LAYERS = {"E2f", "E3f", "D0f", "D1f", "D2f", "E3g", "D0g", "D1g"}
 ONLY = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
 dev = "cuda"
 bf = torch.bfloat16
@@ -39,7 +41,10 @@ LAYERS = [
 
 def bench(name, H, k, C, N, loader, epi, tm=0, nblk=0, iters=20):
     ktab = L.KTAB_PAIR8 if loader == L.LOAD_NCHW3 else L.KTAB_GENERIC
+    wa = WA and name in WA_LAYERS
     ksteps = L.lib.cvae_conv_ksteps(k, C, ktab)
+    if wa:
+        ktab = L.KTAB_BLOCK64
     src2 = None
     if loader == L.LOAD_NCHW3:
         src = torch.rand(B, 3, H, H, device=dev)
@@ -87,7 +92,18 @@ def bench(name, H, k, C, N, loader, epi, tm=0, nblk=0, iters=20):
         b.record(side)
     torch.cuda.synchronize()
     us = a.elapsed_time(b) * 1e3 / iters
-    if os.environ.get("CVAE_COUNTERS"):
+    if os.environ.get("CVAE_COUNTERS") and wa:
+        buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+        L.lib.cvae_conv_wa_debug_counters(buf.data_ptr())
+        L.lib.cvae_conv_gemm(ctypes.byref(d), s)
+        torch.cuda.synchronize()
+        L.lib.cvae_conv_wa_debug_counters(None)
+        c = buf.view(148, 8).cpu().double()
+        c = c[c[:, 0] > 0]
+        m = c.mean(0)
+        print(f"   {name} [wa] ctas={c.shape[0]} MMA thread: total {m[0]:.0f} cyc (max {c[:, 0].max():.0f}), wait acc {m[1]:.0f}, pixels {m[2]:.0f}, "
+              f"weights {m[3]:.0f}, items {m[4]:.1f}, SM clock {m[0] / max(m[5], 1) * 1e3:.0f} MHz")
+    elif os.environ.get("CVAE_COUNTERS"):
         buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
         L.lib.cvae_conv_debug_counters(buf.data_ptr())
         L.lib.cvae_conv_gemm(ctypes.byref(d), s)
@@ -103,6 +119,8 @@ def bench(name, H, k, C, N, loader, epi, tm=0, nblk=0, iters=20):
     return us, flops / us * 1e-6
 
 
+if os.environ.get("WA_TUNE"):
+    L.lib.cvae_conv_wa_tune(*[int(v) for v in os.environ["WA_TUNE"].split(",")])
 tot = 0.0
 for (name, H, k, C, N, loader, epi) in LAYERS:
     if ONLY and name != ONLY:
@@ -125,6 +143,22 @@ for (name, H, k, C, N, loader, epi) in LAYERS:
                     res.append((rr[0], nblk, tm))
         res.sort()
         line += "  | best " + ", ".join(f"n{n}/tm{t}:{u:.1f}" for u, n, t in res[:5])
+        if res and res[0][0] < best[0]:
+            best = (res[0][0], 0)
+    if WA and name in WA_LAYERS and "--wa-sweep" in sys.argv:
+        res = []
+        for cl in (1, 2, 4):
+            for ups in (1, 2):
+                for grid in (0, 148, 144, 132, 112, 96, 74, 72, 64, 48, 36):
+                    if grid % cl:
+                        continue
+                    L.lib.cvae_conv_wa_tune(cl, grid, ups, 0)
+                    rr = bench(name, H, k, C, N, loader, epi, iters=10)
+                    if rr:
+                        res.append((rr[0], cl, grid, ups))
+        L.lib.cvae_conv_wa_tune(0, 0, 0, 0)
+        res.sort()
+        line += "  | best " + ", ".join(f"cl{c}/g{g}/u{u}:{t:.1f}" for t, c, g, u in res[:6])
         if res and res[0][0] < best[0]:
             best = (res[0][0], 0)
     tot += best[0]

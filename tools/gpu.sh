@@ -1,0 +1,11 @@
+#!/bin/bash
+# Retry wrapper around gpurun: the pod answers "transient" (exit 3) while its GPU slots are busy; nothing is charged then.
+# usage: tools/gpu.sh <timeout-seconds> '<command>' [gpus]
+T=$1; CMD=$2; G=${3:-1}
+for i in $(seq 1 40); do
+    if [ "$G" = "1" ]; then /usr/local/graft/bin/gpurun --timeout "$T" -- "$CMD"; else /usr/local/graft/bin/gpurun --gpus "$G" --timeout "$T" -- "$CMD"; fi
+    rc=$?
+    if [ $rc -ne 3 ]; then exit $rc; fi
+    sleep 45
+done
+exit 3
