@@ -32,6 +32,7 @@
 namespace cvae {
 
 int conv_wa_dispatch(const cvae_conv_desc* d, cudaStream_t stream);   // conv_wa.cu
+int64_t conv_wa_workspace_bytes(const cvae_conv_desc* d);
 
 struct ConvArgs {
     int B, H, W, pad, KW;
@@ -632,6 +633,11 @@ static int plan_pipe(const cvae_conv_desc* d, ConvArgs& a, int all_planes, int m
     *n_out = N;
     return CVAE_OK;
 
+}
+
+extern "C" int64_t cvae_conv_gemm_workspace_bytes(const cvae_conv_desc* d) {
+    if (!d) return -1;
+    return d->ktab == CVAE_KTAB_BLOCK64 ? conv_wa_workspace_bytes(d) : 0;
 }
 
 extern "C" int cvae_conv_gemm(const cvae_conv_desc* d, void* stream_) {

@@ -4,6 +4,7 @@
 // One launch packs every layer; it runs at the head of each forward so Adam updates, load_state_dict
 // or any user edit of a parameter are always picked up.
 #include "common.cuh"
+#include "wa_groups.cuh"
 
 namespace cvae {
 
@@ -53,7 +54,8 @@ __device__ float pack_value(const cvae_pack_job& j, long long i, bool& is_bf16) 
     const int ng = (int)((i >> 7) % (NB / 8));
     const long long rest = i / (16LL * NB);
     const int ks = (int)(rest % j.ksteps), nb = (int)(rest / j.ksteps);
-    const int n = nb * NB + ng * 8 + r, k16 = kc * 8 + e;
+    int n = nb * NB + ng * 8 + r;
+    const int k16 = kc * 8 + e;
 
     if (j.kind == CVAE_PACK_PAIR8) {      // encoder conv 0: two taps of an 8-channel padded pixel per K step
         const int c = k16 & 7, half = k16 >> 3;
@@ -66,10 +68,23 @@ __device__ float pack_value(const cvae_pack_job& j, long long i, bool& is_bf16) 
     }
     const int cpt = j.k_channels / 16;  // K steps per tap
     int tap, c;
-    if (j.kind & CVAE_PACK_KORDER_BLOCK64) {   // (64-channel block, tap, 16-channel group): conv_wa.cu streams one block's taps back to back
-        const int taps = j.ksteps / cpt, blk = ks / (taps * 4), rem = ks - blk * taps * 4;
-        tap = rem >> 2;
-        c = blk * 64 + (rem & 3) * 16 + k16;
+    if (j.kind & (CVAE_PACK_KORDER_BLOCK64 | CVAE_PACK_KORDER_BLOCK32)) {
+        // conv_wa.cu: K steps ordered (channel block, tap group, 16-channel step); with tap stacking GEMM row n of a
+        // 128-row block is (channel n / J, jj = n % J) and carries tap dx = s - jj of its group, or zeros
+        const int kb = (j.kind & CVAE_PACK_KORDER_BLOCK64) ? 64 : 32, spu = kb / 16;
+        const int J = (j.kind & CVAE_PACK_STACK4) ? 4 : ((j.kind & CVAE_PACK_STACK2) ? 2 : 1);
+        const int base = j.kind & 0xFF;
+        const int ksize = (base == CVAE_PACK_FWD5 || base == CVAE_PACK_DGRAD5) ? 5 : 3;
+        const int groups = wa_group_count(ksize, J);
+        const int blk = ks / (groups * spu), rem = ks - blk * groups * spu;
+        const int g = rem / spu;
+        c = blk * kb + (rem - g * spu) * 16 + k16;
+        int dy, s, lo;
+        wa_group(ksize, J, g, dy, s, lo);
+        const int nl = n % 128, jj = nl % J, dx = s - jj;
+        if (dx < lo) return 0.f;
+        n = (n / 128) * (128 / J) + nl / J;
+        tap = (dy + ksize / 2) * ksize + dx + ksize / 2;
     } else {
         tap = ks / cpt;
         c = (ks % cpt) * 16 + k16;
@@ -130,9 +145,11 @@ extern "C" int cvae_pack_weights(const cvae_pack_job* jobs, int count, void* str
         CVAE_REQUIRE(jobs[i].src && jobs[i].dst, CVAE_EINVAL, "pack_weights: job %d has a null tensor", i);
         if (jobs[i].kind != CVAE_PACK_FC && jobs[i].kind != CVAE_PACK_DECIN)
             CVAE_REQUIRE(jobs[i].n % 16 == 0 && jobs[i].ksteps > 0, CVAE_EINVAL, "pack_weights: job %d shape", i);
-        if (jobs[i].kind & CVAE_PACK_KORDER_BLOCK64)
-            CVAE_REQUIRE(jobs[i].k_channels % 64 == 0 && (jobs[i].kind & 0xFF) != CVAE_PACK_PAIR8 && (jobs[i].kind & 0xFF) <= CVAE_PACK_PHASE_DGRAD &&
+        if (jobs[i].kind & ~0xFF) {
+            const int kb = (jobs[i].kind & CVAE_PACK_KORDER_BLOCK64) ? 64 : ((jobs[i].kind & CVAE_PACK_KORDER_BLOCK32) ? 32 : 0);
+            CVAE_REQUIRE(kb && jobs[i].k_channels % kb == 0 && (jobs[i].kind & 0xFF) != CVAE_PACK_PAIR8 && (jobs[i].kind & 0xFF) <= CVAE_PACK_PHASE_DGRAD &&
                              jobs[i].n % 128 == 0, CVAE_EINVAL, "pack_weights: job %d cannot be packed block-major", i);
+        }
         pj.job[i] = jobs[i];
         pj.start[i] = total;
         total += cvae_pack_elems(&jobs[i]);

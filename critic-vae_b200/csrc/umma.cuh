@@ -48,8 +48,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Returns false (and raises *fault) when the barrier never flips.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* fault) {
+#pragma unroll 1
     for (uint32_t i = 0; i < kSpinLimit; ++i) {
         if (mbar_try_wait(bar, parity)) return true;
+    }
+    atomicExch(fault, 1);
+    return false;
+}
+
+// The same for roles that are NOT on the critical path (epilogue warps waiting for an accumulator, producers waiting
+// for a free slot): back off between probes so the spinning warp does not take issue slots from the MMA thread that
+// shares its scheduler.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int* fault) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < kSpinLimit; ++i) {
+        if (mbar_try_wait(bar, parity)) return true;
+        __nanosleep(i < 64 ? 32 : 256);
     }
     atomicExch(fault, 1);
     return false;

@@ -30,7 +30,8 @@ class ConvDesc(ctypes.Structure):
                 ("loader", ctypes.c_int32), ("epilogue", ctypes.c_int32), ("ktab", ctypes.c_int32),
                 ("tm", ctypes.c_int32), ("n_block", ctypes.c_int32),
                 ("src", c_void_p), ("src2", c_void_p), ("wpack", c_void_p), ("bias", c_void_p),
-                ("act", c_void_p), ("out", c_void_p), ("stats", c_void_p)]
+                ("act", c_void_p), ("out", c_void_p), ("stats", c_void_p),
+                ("stack", ctypes.c_int32), ("reserved", ctypes.c_int32), ("workspace", c_void_p), ("workspace_bytes", ctypes.c_int64)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -53,7 +54,9 @@ lib.cvae_wgrad_debug_counters.argtypes = [c_void_p]
 lib.cvae_wgrad_debug_counters.restype = None
 lib.cvae_conv_wa_debug_counters.argtypes = [c_void_p]
 lib.cvae_conv_wa_debug_counters.restype = None
-lib.cvae_conv_wa_tune.argtypes = [c_int, c_int, c_int, c_int]
+lib.cvae_conv_wa_tune.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
+lib.cvae_conv_gemm_workspace_bytes.argtypes = [ctypes.POINTER(ConvDesc)]
+lib.cvae_conv_gemm_workspace_bytes.restype = c_i64
 lib.cvae_conv_wa_tune.restype = None
 lib.cvae_conv_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(WgradDesc)]
 lib.cvae_conv_wgrad_workspace_bytes.restype = c_i64
@@ -98,7 +101,7 @@ for _name, (_args, _res) in _SIGS.items():
 
 EXPORTS = ["cvae_last_error", "cvae_version", "cvae_check_device_fault", "cvae_conv_gemm", "cvae_conv_ksteps",
            "cvae_conv_wgrad_workspace_bytes", "cvae_conv_wgrad", "cvae_conv_debug_counters", "cvae_wgrad_debug_counters",
-           "cvae_conv_wa_debug_counters", "cvae_conv_wa_tune"] + list(_SIGS)
+           "cvae_conv_wa_debug_counters", "cvae_conv_wa_tune", "cvae_conv_gemm_workspace_bytes"] + list(_SIGS)
 
 
 def check(rc: int) -> None:
@@ -115,7 +118,7 @@ def stream_ptr():
 LOAD_NHWC, LOAD_NCHW3, LOAD_S2D, LOAD_S2D_NCHW3_DTANH = 0, 1, 2, 3
 EPI_STATS, EPI_BIAS_RELU, EPI_PHASE_BIAS_RELU, EPI_PHASE_BIAS_TANH, EPI_MASK, EPI_PLAIN = 0, 1, 2, 3, 4, 5
 KTAB_GENERIC, KTAB_PAIR8, KTAB_BLOCK64 = 0, 1, 2
-PACK_KORDER_BLOCK64 = 0x100
+PACK_KORDER_BLOCK64, PACK_STACK2, PACK_STACK4, PACK_KORDER_BLOCK32 = 0x100, 0x200, 0x400, 0x800
 WGRAD_5X5, WGRAD_PHASE, WGRAD_SHIFT_FRAMES, WGRAD_SHIFT_PHASE12 = 0, 1, 2, 3
 PACK_FWD5, PACK_DGRAD5, PACK_PAIR8, PACK_PHASE_FWD, PACK_PHASE_DGRAD, PACK_FC, PACK_DECIN = range(7)
 ACT_RELU, ACT_TANH = 0, 1

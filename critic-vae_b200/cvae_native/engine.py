@@ -129,12 +129,26 @@ class VAEEngine:
         # Layers whose GEMM has >= 128 output columns and a source in multiples of 64 channels run the weights-as-A
         # kernel (csrc/conv_wa.cu, CVAE_KTAB_BLOCK64); it wants its K steps packed block-major.  CVAE_NO_WA=1 keeps
         # every layer on the pixels-as-M kernel (A/B comparisons).
-        self.wa_keys = set() if os.environ.get("CVAE_NO_WA") else {"E2f", "E3f", "D0f", "D1f", "D2f", "E3g", "D0g", "D1g"}
+        # key -> (channels per K block, taps stacked into the 128 MMA rows).  Everything but the 3-channel ends of the
+        # network (E0 forward, D4 forward / data gradient) qualifies; the default set is the layers where the
+        # weights-as-A kernel measured faster at batch 256 (profiles/r02_conv_layers.md).  CVAE_WA_ONLY=<keys> picks
+        # another subset, CVAE_WA_ONLY=all takes every eligible layer (A/B comparisons).
+        wa_all = {"E1f": (32, 2), "E2f": (64, 1), "E3f": (64, 1), "D0f": (64, 1), "D1f": (64, 1), "D2f": (64, 1), "D3f": (32, 1),
+                  "E1g": (64, 4), "E2g": (64, 2), "E3g": (64, 1), "D0g": (64, 1), "D1g": (64, 1), "D2g": (32, 2), "D3g": (32, 4)}
+        only = os.environ.get("CVAE_WA_ONLY", "E2f,E3f,E3g,E2g,D0f,D2f,D2g")
+        wa = dict(wa_all) if only == "all" else {k: v for k, v in wa_all.items() if k in only.split(",")}
+        self.wa_keys = {} if os.environ.get("CVAE_NO_WA") else wa
+        self._conv_ws = {}
 
         def add(key, kind, n, ksteps, kch, cout, cin, src, src2=None, dtype=torch.bfloat16, elems=None):
             if key in self.wa_keys:
-                assert kch % 64 == 0 and n % 128 == 0, key
-                kind |= L.PACK_KORDER_BLOCK64
+                kb, J = self.wa_keys[key]
+                assert kch % kb == 0 and (n * J) % 128 == 0, key
+                taps = 25 if kind in (L.PACK_FWD5, L.PACK_DGRAD5) else 9
+                groups = (25 if taps == 25 else 9) if J == 1 else {(25, 2): 15, (25, 4): 10, (9, 2): 6, (9, 4): 3}[(taps, J)]
+                ksteps = (kch // kb) * groups * (kb // 16)
+                n = n * J
+                kind |= (L.PACK_KORDER_BLOCK64 if kb == 64 else L.PACK_KORDER_BLOCK32) | {1: 0, 2: L.PACK_STACK2, 4: L.PACK_STACK4}[J]
             numel = elems if elems is not None else n * ksteps * 16
             dst = torch.zeros(numel, dtype=dtype, device=dev)
             self.packed[key] = dst
@@ -209,8 +223,18 @@ class VAEEngine:
     def _ktab(self, key):
         return L.KTAB_BLOCK64 if key in self.wa_keys else L.KTAB_GENERIC
 
-    def _conv(self, **kw):
+    def _conv(self, key=None, **kw):
         d = L.ConvDesc(**{k: (_ptr(v) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
+        if key in self.wa_keys:
+            d.ktab, d.stack = L.KTAB_BLOCK64, self.wa_keys[key][1]
+            need = int(L.lib.cvae_conv_gemm_workspace_bytes(ctypes.byref(d)))
+            if need < 0:
+                L.check(need)
+            if need:   # split-K scratch, zero-initialised once: the kernel leaves its arrival counters at zero
+                ws = self._conv_ws.get((key, d.batch))
+                if ws is None or ws.numel() < need:
+                    ws = self._conv_ws[(key, d.batch)] = torch.zeros(need, dtype=torch.uint8, device=self.device)
+                d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
         self._timed("conv_gemm", lambda: L.check(L.lib.cvae_conv_gemm(ctypes.byref(d), L.stream_ptr())))
 
     def encode(self, x, training, ws, pack=True):
@@ -228,8 +252,8 @@ class VAEEngine:
                 self._conv(batch=B, height=h, width=h, ksize=5, src_channels=8, n_total=co, loader=L.LOAD_NCHW3,
                            epilogue=L.EPI_STATS, ktab=L.KTAB_PAIR8, src=x, wpack=self.packed["E0f"], out=ws.c[0], stats=stats)
             else:
-                self._conv(batch=B, height=h, width=h, ksize=5, src_channels=ci, n_total=co, loader=L.LOAD_NHWC,
-                           epilogue=L.EPI_STATS, ktab=self._ktab(f"E{i}f"), src=ws.a[i - 1], wpack=self.packed[f"E{i}f"],
+                self._conv(f"E{i}f", batch=B, height=h, width=h, ksize=5, src_channels=ci, n_total=co, loader=L.LOAD_NHWC,
+                           epilogue=L.EPI_STATS, ktab=L.KTAB_GENERIC, src=ws.a[i - 1], wpack=self.packed[f"E{i}f"],
                            out=ws.c[i], stats=stats)
             cname, bname = f"encoder.model.{ENC_CONV_IDX[i]}", f"encoder.model.{ENC_BN_IDX[i]}"
             L.check(L.lib.cvae_bn_finalize(co, B * h * h, int(training), _ptr(stats), _ptr(self.view(bname + ".weight")),
@@ -254,12 +278,12 @@ class VAEEngine:
                                       _ptr(ws.kld_partial) if sample else None, s))
         L.check(L.lib.cvae_decin_fwd(B, _ptr(ws.zc), _ptr(self.packed["decin"]), _ptr(ws.h0), s))
         bias = lambda i: self.view(f"decoder.model.{DEC_CONV_IDX[i]}.bias")
-        self._conv(batch=B, height=4, width=4, ksize=5, src_channels=256, n_total=128, loader=L.LOAD_NHWC,
-                   epilogue=L.EPI_BIAS_RELU, ktab=self._ktab("D0f"), src=ws.h0, wpack=self.packed["D0f"], out=ws.d[0], bias=bias(0))
+        self._conv("D0f", batch=B, height=4, width=4, ksize=5, src_channels=256, n_total=128, loader=L.LOAD_NHWC,
+                   epilogue=L.EPI_BIAS_RELU, ktab=L.KTAB_GENERIC, src=ws.h0, wpack=self.packed["D0f"], out=ws.d[0], bias=bias(0))
         for i in (1, 2, 3):
             ci, co, h = DEC[i]
-            self._conv(batch=B, height=h, width=h, ksize=3, src_channels=ci, n_total=4 * co, loader=L.LOAD_NHWC,
-                       epilogue=L.EPI_PHASE_BIAS_RELU, ktab=self._ktab(f"D{i}f"), src=ws.d[i - 1], wpack=self.packed[f"D{i}f"],
+            self._conv(f"D{i}f", batch=B, height=h, width=h, ksize=3, src_channels=ci, n_total=4 * co, loader=L.LOAD_NHWC,
+                       epilogue=L.EPI_PHASE_BIAS_RELU, ktab=L.KTAB_GENERIC, src=ws.d[i - 1], wpack=self.packed[f"D{i}f"],
                        out=ws.d[i], bias=bias(i))
         self._conv(batch=B, height=32, width=32, ksize=3, src_channels=32, n_total=16, loader=L.LOAD_NHWC,
                    epilogue=L.EPI_PHASE_BIAS_TANH, ktab=L.KTAB_GENERIC, src=ws.d[3], wpack=self.packed["D4f"],
@@ -342,12 +366,12 @@ class VAEEngine:
             ci, co, h = DEC[i]
             self._wgrad(g, f"{dm}{DEC_CONV_IDX[i]}", kind=L.WGRAD_PHASE, batch=B, height=h, width=h, cout=co, cin=ci,
                         x=ws.d[i - 1], dy=ws.g_d[i])
-            self._conv(batch=B, height=h, width=h, ksize=3, src_channels=4 * co, n_total=ci, loader=L.LOAD_S2D,
-                       epilogue=L.EPI_MASK, ktab=self._ktab(f"D{i}g"), src=ws.g_d[i], wpack=self.packed[f"D{i}g"],
+            self._conv(f"D{i}g", batch=B, height=h, width=h, ksize=3, src_channels=4 * co, n_total=ci, loader=L.LOAD_S2D,
+                       epilogue=L.EPI_MASK, ktab=L.KTAB_GENERIC, src=ws.g_d[i], wpack=self.packed[f"D{i}g"],
                        out=ws.g_d[i - 1], act=ws.d[i - 1])
         self._wgrad(g, dm + "0", kind=L.WGRAD_5X5, batch=B, height=4, width=4, cout=128, cin=256, x=ws.h0, dy=ws.g_d[0])
-        self._conv(batch=B, height=4, width=4, ksize=5, src_channels=128, n_total=256, loader=L.LOAD_NHWC,
-                   epilogue=L.EPI_PLAIN, ktab=self._ktab("D0g"), src=ws.g_d[0], wpack=self.packed["D0g"], out=ws.g_h0)
+        self._conv("D0g", batch=B, height=4, width=4, ksize=5, src_channels=128, n_total=256, loader=L.LOAD_NHWC,
+                   epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_d[0], wpack=self.packed["D0g"], out=ws.g_h0)
         self._leaf(lambda st: L.check(L.lib.cvae_decin_bwd(B, _ptr(ws.g_h0), _ptr(ws.zc), None, None,
                                                            _ptr(G("decoder.decoder_input.weight")),
                                                            _ptr(G("decoder.decoder_input.bias")), st)))
@@ -370,8 +394,8 @@ class VAEEngine:
                 self._wgrad(g, cname, kind=L.WGRAD_SHIFT_FRAMES, batch=B, height=64, width=64, cout=32, cin=3, x=x, dy=ws.g_c[0])
             else:
                 self._wgrad(g, cname, kind=L.WGRAD_5X5, batch=B, height=h, width=h, cout=co, cin=ci, x=ws.a[i - 1], dy=ws.g_c[i])
-                self._conv(batch=B, height=h, width=h, ksize=5, src_channels=co, n_total=ci, loader=L.LOAD_NHWC,
-                           epilogue=L.EPI_PLAIN, ktab=self._ktab(f"E{i}g"), src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
+                self._conv(f"E{i}g", batch=B, height=h, width=h, ksize=5, src_channels=co, n_total=ci, loader=L.LOAD_NHWC,
+                           epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
         if self._side_used:
             torch.cuda.current_stream().wait_stream(self.side_stream)
         if self._fold_used:

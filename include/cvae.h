@@ -57,9 +57,10 @@ enum cvae_epilogue {
 enum cvae_ktab {
     CVAE_KTAB_GENERIC = 0,
     CVAE_KTAB_PAIR8 = 1,   /* 8-channel source, two taps per K step */
-    CVAE_KTAB_BLOCK64 = 2  /* weights packed block-major (CVAE_PACK_KORDER_BLOCK64): run the weights-as-A kernel (conv_wa.cu):
-                              src_channels % 64 == 0, n_total % 128 == 0, loader NHWC (or S2D with 4 x 64 channels), any
-                              epilogue except PHASE_BIAS_TANH.  Same results as the GENERIC path. */
+    CVAE_KTAB_BLOCK64 = 2  /* weights packed block-major (CVAE_PACK_KORDER_BLOCK64 / _BLOCK32, optionally CVAE_PACK_STACKx): run the
+                              weights-as-A kernel (conv_wa.cu).  src_channels % 32 == 0 (S2D: 4 x 64 or 4 x 32), n_total x stack in
+                              {128, 256}, loader NHWC or S2D, any epilogue except PHASE_BIAS_TANH (stack > 1: STATS, MASK, PLAIN).
+                              Same results as the GENERIC path. */
 };
 
 typedef struct {
@@ -77,12 +78,22 @@ typedef struct {
     const void* act;
     void* out;
     double* stats;         /* [2][n_total], accumulated with atomics (zero it first) */
+    /* CVAE_KTAB_BLOCK64 only (zero otherwise) */
+    int32_t stack;         /* tap stacking factor the weights were packed with: 0/1, 2 (n_total = 64) or 4 (n_total = 32) */
+    int32_t reserved;
+    void* workspace;       /* split-K scratch of >= cvae_conv_gemm_workspace_bytes(d) bytes, ZERO-INITIALISED once by the caller
+                              (the kernel leaves its arrival counters at zero); may be NULL when that query returns 0 */
+    int64_t workspace_bytes;
 } cvae_conv_desc;
 
 int cvae_conv_gemm(const cvae_conv_desc* d, void* stream);
-/* tuning / test hook for the weights-as-A kernel: force cluster size (1, 2, 4), grid size, (block, tap) units per
- * weight stage and a minimum number of tiles per CTA; 0 = automatic.  Process-wide. */
-void cvae_conv_wa_tune(int cluster, int grid, int units_per_stage, int tiles_per_cta);
+/* bytes of cvae_conv_desc.workspace this descriptor needs (0 for every GENERIC / PAIR8 call and for weights-as-A
+ * calls that do not split K; pointers in the descriptor are not read); negative on an unsupported shape */
+int64_t cvae_conv_gemm_workspace_bytes(const cvae_conv_desc* d);
+/* tuning / test hook for the weights-as-A kernel: force cluster size (1, 2, 4), grid size, (block, tap group) units
+ * per weight stage, a minimum number of tiles per CTA, the K split (1, 2, 4) and the weight fetch (1: 1-D bulk copies,
+ * 2: 2-D tensor-map boxes); 0 = automatic.  Process-wide. */
+void cvae_conv_wa_tune(int cluster, int grid, int units_per_stage, int tiles_per_cta, int ksplit, int weight_load);
 /* profiling aid: device buffer of >= 8 * 148 uint64 cycle counters of the weights-as-A kernel's MMA thread (NULL = off) */
 void cvae_conv_wa_debug_counters(void* device_buf);
 /* profiling aid: device buffer of >= 8 * 148 uint64 cycle counters written by the pipelined kernel (NULL = off) */
@@ -134,9 +145,15 @@ enum cvae_pack_kind {
     CVAE_PACK_FC = 5,          /* src = fc_mu.weight, src2 = fc_var.weight -> fp32 [4096 nhwc][64]    */
     CVAE_PACK_DECIN = 6        /* src = decoder_input.weight, src2 = bias -> fp32 [34][4096 nhwc]     */
 };
-/* OR-ed into `kind` of the conv forms: K steps ordered (64-channel block, tap, 16-channel group) instead of
- * (tap, 16-channel group) -- the order the weights-as-A kernel (CVAE_KTAB_BLOCK64) streams; k_channels % 64 == 0 */
+/* OR-ed into `kind` of the conv forms for the weights-as-A kernel (CVAE_KTAB_BLOCK64):
+ *   KORDER_BLOCK64 / _BLOCK32: K steps ordered (64- / 32-channel block, tap group, 16-channel group) instead of
+ *     (tap, 16-channel group); k_channels a multiple of 64 / 32;
+ *   STACK2 / STACK4: tap stacking -- GEMM row r of a 128-row block is (channel r / J, j = r % J) and carries tap
+ *     dx = s - j of the group (csrc/wa_groups.cuh); `n` is then J x the layer's GEMM width (a multiple of 128). */
 #define CVAE_PACK_KORDER_BLOCK64 0x100
+#define CVAE_PACK_STACK2 0x200
+#define CVAE_PACK_STACK4 0x400
+#define CVAE_PACK_KORDER_BLOCK32 0x800
 typedef struct {
     int32_t kind, n, ksteps, k_channels, cout, cin;
     const void* src;

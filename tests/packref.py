@@ -68,12 +68,43 @@ def pack_generic(Wg):
     return pack_kblocks(Wg.reshape(N, T * (C // 16), 16))
 
 
-def pack_block64(Wg):
-    """Wg [N][taps][C] (C % 64 == 0, N % 128 == 0) -> packed bf16 with K steps ordered (64-channel block, tap,
-    16-channel group): the order conv_wa.cu streams (CVAE_PACK_KORDER_BLOCK64)."""
+def wa_groups(ksize, J):
+    """Tap groups of the weights-as-A kernel (csrc/wa_groups.cuh): list of (dy, s, lo) in (filter row, chunk) order."""
+    pad, nc = ksize // 2, (ksize + J - 1) // J
+    out = []
+    for row in range(ksize):
+        for k in range(nc):
+            lo = -pad + k * J
+            out.append((row - pad, min(lo + J - 1, pad), lo))
+    return out
+
+
+def pack_wa(Wg, kb=64, J=1):
+    """Wg [N][taps][C] (taps = 25 or 9, C % kb == 0, N * J % 128 == 0) -> packed bf16 for conv_wa.cu: K steps ordered
+    (kb-channel block, tap group, 16-channel step); GEMM row r of a 128-row block = (channel r // J, j = r % J) carrying
+    tap dx = s - j of its group or zeros (CVAE_PACK_KORDER_BLOCK64/32 | CVAE_PACK_STACK2/4)."""
     N, T, C = Wg.shape
-    x = Wg.reshape(N, T, C // 64, 4, 16).permute(0, 2, 1, 3, 4).reshape(N, (C // 64) * T * 4, 16)
-    return pack_kblocks(x)
+    ksize = 5 if T == 25 else 3
+    pad, groups, spu, nblk = ksize // 2, wa_groups(ksize, J), kb // 16, C // kb
+    rows = N * J
+    Wk = torch.zeros(rows, nblk, len(groups), spu, 16)
+    r = torch.arange(rows)
+    ch = (r // 128) * (128 // J) + (r % 128) // J
+    jj = (r % 128) % J
+    for gi, (dy, s, lo) in enumerate(groups):
+        for j in range(J):
+            dx = s - j
+            if dx < lo:
+                continue
+            tap = (dy + pad) * ksize + dx + pad
+            sel = jj == j
+            Wk[sel, :, gi] = Wg[ch[sel], tap].reshape(-1, nblk, spu, 16)
+    return pack_kblocks(Wk.reshape(rows, nblk * len(groups) * spu, 16))
+
+
+def pack_block64(Wg):
+    """pack_wa without stacking, 64-channel blocks (CVAE_PACK_KORDER_BLOCK64)."""
+    return pack_wa(Wg, 64, 1)
 
 
 def pack_pair8_e0(W):

@@ -12,7 +12,11 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 B = int(args[0]) if args else 256
 SWEEP = "--sweep" in sys.argv
 WA = "--wa" in sys.argv          # run the layers the weights-as-A kernel covers through it (CVAE_KTAB_BLOCK64)
-WA_LAYERS = {"E2f", "E3f", "D0f", "D1f", "D2f", "E3g", "D0g", "D1g"}
+WA_LAYERS = {"E1f": (32, 2), "E2f": (64, 1), "E3f": (64, 1), "D0f": (64, 1), "D1f": (64, 1), "D2f": (64, 1), "D3f": (32, 1),
+             "E1g": (64, 4), "E2g": (64, 2), "E3g": (64, 1), "D0g": (64, 1), "D1g": (64, 1), "D2g": (32, 2), "D3g": (32, 4)}
+if os.environ.get("CVAE_WA_ONLY") is not None:
+    WA_LAYERS = {k: v for k, v in WA_LAYERS.items() if k in os.environ["CVAE_WA_ONLY"].split(",")}
+_WS = {}
 ONLY = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
 dev = "cuda"
 bf = torch.bfloat16
@@ -43,8 +47,12 @@ def bench(name, H, k, C, N, loader, epi, tm=0, nblk=0, iters=20):
     ktab = L.KTAB_PAIR8 if loader == L.LOAD_NCHW3 else L.KTAB_GENERIC
     wa = WA and name in WA_LAYERS
     ksteps = L.lib.cvae_conv_ksteps(k, C, ktab)
+    stack = 0
     if wa:
         ktab = L.KTAB_BLOCK64
+        kb, stack = WA_LAYERS[name]
+        groups = k * k if stack == 1 else {(5, 2): 15, (5, 4): 10, (3, 2): 6, (3, 4): 3}[(k, stack)]
+        ksteps = (C // kb) * groups * (kb // 16) * stack      # x stack: the packed GEMM has N * stack rows
     src2 = None
     if loader == L.LOAD_NCHW3:
         src = torch.rand(B, 3, H, H, device=dev)
@@ -66,11 +74,16 @@ def bench(name, H, k, C, N, loader, epi, tm=0, nblk=0, iters=20):
     act = torch.randn(B, H, H, N, device=dev).to(bf) if epi == L.EPI_MASK else None
     stats = torch.zeros(2 * N, dtype=torch.float64, device=dev) if epi == L.EPI_STATS else None
     d = L.ConvDesc(batch=B, height=H, width=H, ksize=k, src_channels=C, n_total=N, loader=loader, epilogue=epi,
-                   ktab=ktab, tm=tm, n_block=nblk, src=src.data_ptr(), src2=src2.data_ptr() if src2 is not None else None,
+                   ktab=ktab, tm=tm, n_block=nblk, stack=stack, src=src.data_ptr(), src2=src2.data_ptr() if src2 is not None else None,
                    wpack=wp.data_ptr(), bias=bias.data_ptr(),
                    act=act.data_ptr() if act is not None else None, out=out.data_ptr(),
                    stats=stats.data_ptr() if stats is not None else None)
     s = L.stream_ptr()
+    need = int(L.lib.cvae_conv_gemm_workspace_bytes(ctypes.byref(d)))
+    if need > 0:
+        if "b" not in _WS or _WS["b"].numel() < need:
+            _WS["b"] = torch.zeros(need, dtype=torch.uint8, device=dev)
+        d.workspace, d.workspace_bytes = _WS["b"].data_ptr(), _WS["b"].numel()
     rc = L.lib.cvae_conv_gemm(ctypes.byref(d), s)
     if rc != 0:
         return None
@@ -102,7 +115,7 @@ def bench(name, H, k, C, N, loader, epi, tm=0, nblk=0, iters=20):
         c = c[c[:, 0] > 0]
         m = c.mean(0)
         print(f"   {name} [wa] ctas={c.shape[0]} MMA thread: total {m[0]:.0f} cyc (max {c[:, 0].max():.0f}), wait acc {m[1]:.0f}, pixels {m[2]:.0f}, "
-              f"weights {m[3]:.0f}, items {m[4]:.1f}, SM clock {m[0] / max(m[5], 1) * 1e3:.0f} MHz")
+              f"weights {m[3]:.0f}, items {m[4]:.1f}, SM clock {m[0] / max(m[5], 1) * 1e3:.0f} MHz | epilogue {m[6]:.0f} (split-K reduce max {c[:, 7].max():.0f})")
     elif os.environ.get("CVAE_COUNTERS"):
         buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
         L.lib.cvae_conv_debug_counters(buf.data_ptr())
@@ -147,18 +160,18 @@ for (name, H, k, C, N, loader, epi) in LAYERS:
             best = (res[0][0], 0)
     if WA and name in WA_LAYERS and "--wa-sweep" in sys.argv:
         res = []
-        for cl in (1, 2, 4):
-            for ups in (1, 2):
+        for ksp in (1, 2, 4):
+            for ups in (1, 2, 4):
                 for grid in (0, 148, 144, 132, 112, 96, 74, 72, 64, 48, 36):
-                    if grid % cl:
+                    if grid % ksp:
                         continue
-                    L.lib.cvae_conv_wa_tune(cl, grid, ups, 0)
+                    L.lib.cvae_conv_wa_tune(1, grid, ups, 0, ksp, int(os.environ.get("WA_WLOAD", "0")))
                     rr = bench(name, H, k, C, N, loader, epi, iters=10)
                     if rr:
-                        res.append((rr[0], cl, grid, ups))
-        L.lib.cvae_conv_wa_tune(0, 0, 0, 0)
+                        res.append((rr[0], ksp, grid, ups))
+        L.lib.cvae_conv_wa_tune(0, 0, 0, 0, 0, 0)
         res.sort()
-        line += "  | best " + ", ".join(f"cl{c}/g{g}/u{u}:{t:.1f}" for t, c, g, u in res[:6])
+        line += "  | best " + ", ".join(f"k{c}/g{g}/u{u}:{t:.1f}" for t, c, g, u in res[:6])
         if res and res[0][0] < best[0]:
             best = (res[0][0], 0)
     tot += best[0]
