@@ -31,9 +31,18 @@ E0_FLOPS = 19_660_800             # encoder conv 0 needs no data-gradient
 CRITIC_CKPT = os.path.join(ROOT, "critic-vae_b200", "saved-networks",
                            "critic-rewidx=1-cepochs=15-datamode=trunk-datasize=99999-shift=12-chfak=1-dropout=0.3.pt")
 METRIC = "VAE train frames/s (fwd+bwd+loss+Adam)"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the family's launches of one step) from the
-# ncu --set full capture summarised in profiles/r01_gemm_full_v2.md (batch 256)
-NCU_TRAFFIC = {"conv_gemm": 13.24e6, "conv_wgrad": 27.80e6}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed
+    summary of the CURRENT round's `ncu --set full` capture (profiles/r02_ncu_traffic.json, written by
+    tools/ncu_summary.py); None when there is no capture of the kernels as they are now."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}, None
+    with open(path) as f:
+        d = json.load(f)
+    return d.get("bytes_per_launch", {}), d.get("source")
 
 
 def peaks():
@@ -63,7 +72,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         self.stop_flag.set()
@@ -116,13 +125,15 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 64
+    batch = args.batch            # the same per-step batch as the B200 arm (256): same config on both arms
     rate, sec, _ = cpu_train_step_rate(batch, args.steps, args.warmup, threads)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Critic-VAE training step (critic+fwd+MS-SSIM/KLD+bwd+Adam), 64x64x3 synthetic frames, "
-                                   "random-init VAE, shipped critic; bounded sample: batch 64 per step on host cores"},
+            "config": {"workload": "BASELINE.json configs[1]: Critic-VAE training step (critic+fwd+MS-SSIM/KLD+bwd+Adam), "
+                                   f"batch {batch} per GPU, 64x64x3 synthetic frames, random-init VAE (seed 0), shipped critic",
+                       "per_gpu_batch": batch, "global_batch": batch, "parallelism": "host cores",
+                       "note": "the reference's own algorithm (oracle port, torch CPU fp32) on the host cores; every step is one full batch"},
             "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} training steps of batch {batch} (oracle/critic_vae_oracle.py, torch CPU fp32)"},
             "e2e": {"value": rate, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -224,6 +235,112 @@ def latent_secondary(device, hbm_peak):
     return {"rows": N, "algorithmic_bytes_per_row": 520, "achieved_GBps": gbs, "hbm_peak_GBps": hbm_peak, "frac": gbs / hbm_peak}
 
 
+def gpu_baseline(device, batch, steps=20, warmup=5):
+    """The kernel to beat: the reference's algorithm through STOCK PyTorch / cuDNN / cuBLAS on
+    the same B200 -- the oracle's functional restatement (F.conv2d, F.batch_norm, F.max_pool2d, F.interpolate, the
+    MS-SSIM pyramid, autograd, torch.optim.Adam) with its tensors on the GPU.  Variants: fp32 (TF32 off), TF32,
+    bf16 autocast + channels_last; each eager and as one CUDA graph.  None of this repo's kernels run here."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import critic_vae_oracle as O
+    import synth
+    out = {"batch": batch, "what": "oracle/critic_vae_oracle.py (torch functional ops + autograd) on cuda, torch.optim.Adam(capturable)",
+           "variants": {}}
+    crit = {k: v.to(device) for k, v in torch.load(CRITIC_CKPT, map_location="cpu").items()}
+    x = synth.make_frames(64, seed=100).repeat((batch + 63) // 64, 1, 1, 1)[:batch].to(device)
+    eps = torch.randn(batch, 32, device=device)
+
+    def make_step(mode):
+        enc, dec = synth.make_vae_state(0)
+        enc = {k: v.to(device) for k, v in enc.items()}
+        dec = {k: v.to(device) for k, v in dec.items()}
+        params = [enc[k].requires_grad_(True) for k in O.PARAM_KEYS_ENC] + [dec[k].requires_grad_(True) for k in O.PARAM_KEYS_DEC]
+        opt = torch.optim.Adam(params, lr=5e-5, capturable=True)
+        xin = x.contiguous(memory_format=torch.channels_last) if mode == "bf16" else x
+
+        def step():
+            opt.zero_grad(set_to_none=False)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+                with torch.no_grad():
+                    pred = O.critic_forward(crit, xin)
+                _, mu, logvar, recon = O.vae_forward(enc, dec, xin, pred, eps, training=True, update_stats=True)
+            losses = O.vae_loss(x, mu.float(), logvar.float(), recon.float())
+            losses["total_loss"].backward()
+            opt.step()
+            return losses["total_loss"]
+        return step
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    old_tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    old_bench = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        for mode in ("fp32", "tf32", "bf16"):
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = (mode != "fp32")
+            for graphed in (False, True):
+                name = f"{mode}_{'graph' if graphed else 'eager'}"
+                try:
+                    step = make_step(mode)
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        for _ in range(warmup):
+                            loss = step()
+                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.synchronize()
+                    fn = step
+                    if graphed:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            loss = step()
+                        fn = g.replay
+                        fn()
+                    ms = timed(fn, steps)
+                    out["variants"][name] = {"ms_per_step": ms, "frames_per_s": batch / (ms * 1e-3), "loss": float(loss)}
+                except Exception as exc:      # a variant that stock PyTorch cannot run (e.g. graph capture) is reported, not fatal
+                    out["variants"][name] = {"error": repr(exc)[:160]}
+                torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old_tf32
+        torch.backends.cudnn.benchmark = old_bench
+    ok = [v for v in out["variants"].values() if "ms_per_step" in v]
+    if ok:
+        best = min(ok, key=lambda v: v["ms_per_step"])
+        out["best_ms_per_step"] = best["ms_per_step"]
+        out["best_frames_per_s"] = best["frames_per_s"]
+    return out
+
+
+def dataset_secondary(device):
+    """BASELINE.json configs[4]: the `-dataset` path (vae_utility.py:416-443) on 8192 host frames per call: critic value of
+    every frame, balanced selection, reconstructions with the critic value and with 0 of the selection."""
+    import synth
+    import vae_utility as U
+    vae, critic = build_modules(device)
+    vae.eval()
+    n = 8192
+    povs = (synth.make_frames(256, seed=50).permute(0, 2, 3, 1) * 255).round().to(torch.uint8).numpy()
+    povs = np.tile(povs, (n // 256, 1, 1, 1))
+    U.dataset_from_trajectory(povs, critic, recon_dset=True, vae=vae)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        ds = U.dataset_from_trajectory(povs, critic, recon_dset=True, vae=vae)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    return {"frames_per_s": n / dt, "frames_per_call": n, "reconstructions_per_call": len(ds),
+            "workload": "BASELINE.json configs[4]: host uint8 frames -> critic scores (8192) -> balanced selection -> recon(pred), recon(0) "
+                        "of the selection -> host float32 arrays (vae_utility.dataset_from_trajectory)"}
+
+
 def run_b200(args):
     import torch.distributed as dist
     import synth
@@ -288,41 +405,15 @@ def run_b200(args):
     final_loss = [float(v) for v in losses.cpu()]
     vae._engine.check_fault()
 
-    # ---- timed: end to end (pinned host uint8 frames -> H2D -> step -> D2H loss), double buffered ------
-    copy_stream = torch.cuda.Stream()
-    stage = [torch.empty(B, 64, 64, 3, dtype=torch.uint8, device=device) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    loss_host = [torch.empty(3, pin_memory=True) for _ in range(2)]
-    loss_done = [torch.cuda.Event() for _ in range(2)]
-
-    def issue_copy(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[i % 2])
-            stage[i % 2].copy_(host_batches[i % R], non_blocking=True)
-            ready[i % 2].record(copy_stream)
+    # ---- timed: end to end through the product's loader (pinned host uint8 frames -> H2D -> step -> D2H loss) ------
+    from cvae_native.loader import FrameStager
+    stager = FrameStager(step, eps_generator=gen)
 
     def e2e_loop(n):
-        cur = torch.cuda.current_stream()
-        for b in range(2):
-            consumed[b].record(cur)
-        issue_copy(0)
         seen = 0.0
-        for i in range(n):
-            if i + 1 < n:
-                issue_copy(i + 1)
-            cur.wait_event(ready[i % 2])
-            step.load(frames_u8=stage[i % 2])
-            consumed[i % 2].record(cur)
-            step.eps.normal_(generator=gen)
-            out = step.run(from_u8=True)
-            loss_host[i % 2].copy_(out, non_blocking=True)
-            loss_done[i % 2].record(cur)
-            if i > 0:                                   # read the previous step's loss on the host
-                loss_done[(i - 1) % 2].synchronize()
-                seen += float(loss_host[(i - 1) % 2][0])
-        loss_done[(n - 1) % 2].synchronize()
-        return seen + float(loss_host[(n - 1) % 2][0])
+        for loss in stager.run(host_batches[i % R] for i in range(n)):
+            seen += float(loss[0])                      # the host reads every step's loss
+        return seen
 
     e2e_loop(max(args.warmup, 3))
     barrier()
@@ -335,6 +426,7 @@ def run_b200(args):
     e2e_s = e2e_s.item()
     clocks = sampler.summary() if rank == 0 else None
 
+    launches_per_step = int(step.launches_per_step)
     # ---- per-kernel-family CUDA-event pass (eager, same stream) for the roofline -----------------------
     eng = vae._engine
     fam = {}
@@ -351,22 +443,51 @@ def run_b200(args):
     fam_ms = {k: sum(v) / n_it for k, v in fam.items()}              # ms per step per family
     fam_calls = {k: len(v) // n_it for k, v in fam.items()}
     tf_peak, hbm_peak, peak_src = peaks()
+    traffic, traffic_src = ncu_traffic()
     flops = {"conv_gemm": B * (2 * CONV_FLOPS - E0_FLOPS), "conv_wgrad": B * CONV_FLOPS}
     dominant = max(fam_ms, key=fam_ms.get)
     ach = flops[dominant] / (fam_ms[dominant] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": dominant, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": NCU_TRAFFIC.get(dominant) if B == 256 else None, "traffic_unit": "bytes per launch (ncu, profiles/r01_gemm_full_v2.md)",
+                "traffic": traffic.get(dominant) if B == 256 else None, "traffic_unit": f"bytes per launch (ncu --set full, {traffic_src})",
                 "peak_source": peak_src,
                 "launches_per_step": fam_calls[dominant], "ms_per_step_in_kernel": fam_ms[dominant],
                 "families": {k: {"ms_per_step": fam_ms[k], "launches": fam_calls[k],
                                  "achieved_tflops": flops[k] / (fam_ms[k] * 1e-3) / 1e12} for k in fam_ms}}
 
+    # ---- BASELINE.json configs[3]: global batch 4096 split over the N GPUs (strong scaling), N > 1 only ----------------
+    cfg4 = None
+    if world > 1 and 4096 % world == 0 and not args.no_secondary:
+        Bg = 4096 // world
+        del step
+        torch.cuda.empty_cache()
+        step4 = TrainStep(vae, critic, Bg, lr=5e-5, process_group=pg)
+        f4 = frames[:64].repeat((Bg + 63) // 64, 1, 1, 1)[:Bg].contiguous().to(device)
+        step4.load(frames=f4)
+        for _ in range(3):
+            step4.eps.normal_(generator=gen)
+            step4.run()
+        barrier()
+        n4 = max(5, min(args.steps, 25))       # 25 steps of 4096 = the 100k-frame epoch of configs[3]
+        e0.record()
+        for _ in range(n4):
+            step4.eps.normal_(generator=gen)
+            step4.run()
+        e1.record()
+        barrier()
+        t4 = torch.tensor([e0.elapsed_time(e1)], device=device)
+        dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        cfg4 = {"global_batch": 4096, "per_gpu_batch": Bg, "steps": n4, "ms_per_step": t4.item() / n4,
+                "frames_per_s": 4096 * n4 / (t4.item() * 1e-3), "scaling": "strong",
+                "workload": "BASELINE.json configs[3]: data-parallel training step, global batch 4096 (25 steps = one pass over 100k "
+                            "synthetic frames), NCCL gradient all-reduce"}
+        vae._engine.check_fault()
+        step = step4
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     cpu_threads = os.cpu_count() or 1
-    cpu_rate, cpu_sec, cpu_steps = cpu_train_step_rate(64, 4, 1, cpu_threads, budget_s=12.0)
+    cpu_rate, cpu_sec, cpu_steps = cpu_train_step_rate(B, 2, 1, cpu_threads, budget_s=12.0)
     step_ms = ms / args.steps
     value = world * B * args.steps / (ms * 1e-3)
     line = {
@@ -379,15 +500,29 @@ def run_b200(args):
                    "l2": f"{R} rotating input batches; per-step activation+gradient working set ~{B * 1.6:.0f} MB > 126 MB L2",
                    "step_flops_algorithmic": B * TRAIN_FLOPS, "final_loss": final_loss},
         "clocks": clocks,
-        "e2e": {"value": world * B * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": B * 64 * 64 * 3,
-                "d2h_bytes_per_step": 12, "input": "uint8 HWC frames in pinned host memory, double-buffered H2D on a copy stream"},
-        "gpu_launches": int(step.launches_per_step) * args.steps,
+        "e2e": {"value": world * B * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": stager.h2d_bytes_per_step,
+                "d2h_bytes_per_step": stager.d2h_bytes_per_step,
+                "input": "uint8 HWC frames in pinned host memory through cvae_native.loader.FrameStager (double-buffered H2D on a copy "
+                         "stream, uint8 -> fp32 inside the step graph), every step's loss read on the host"},
+        "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "step_tensor_frac": (B * TRAIN_FLOPS / (step_ms * 1e-3) / 1e12) / tf_peak,
         "cpu_baseline": {"value": cpu_rate, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
-                         "sample": f"{cpu_steps} training steps of batch 64 in ~12 s (oracle/critic_vae_oracle.py, torch CPU fp32), same step definition"},
+                         "sample": f"{cpu_steps} training steps of batch {B} in ~{cpu_steps * cpu_sec:.0f} s (oracle/critic_vae_oracle.py, torch CPU fp32), same step definition"},
     }
+    if cfg4 is not None:
+        line["cfg4"] = cfg4
     if world == 1 and not args.no_secondary:
+        try:
+            line["gpu_baseline"] = gpu_baseline(device, B)
+            if "best_frames_per_s" in line["gpu_baseline"]:
+                line["gpu_baseline"]["speedup_vs_best_stock_pytorch"] = value / line["gpu_baseline"]["best_frames_per_s"]
+        except Exception as exc:
+            line["gpu_baseline"] = {"error": repr(exc)[:200]}
+        try:
+            line["dataset_path"] = dataset_secondary(device)
+        except Exception as exc:
+            line["dataset_path"] = {"error": repr(exc)[:200]}
         try:
             del step
             torch.cuda.empty_cache()

@@ -39,6 +39,14 @@ class TrainStep:
         dev = self.eng.device
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        if self.world > 1:
+            # every rank must start from rank 0's parameters, optimizer state and BatchNorm buffers: identical seeding is
+            # not a contract (a checkpoint loaded on one rank, a different init order) and a mismatch diverges silently
+            eng = self.eng
+            if eng.exp_avg is None:
+                eng.exp_avg, eng.exp_avg_sq = torch.zeros_like(eng.flat), torch.zeros_like(eng.flat)
+            for t in [eng.flat, eng.exp_avg, eng.exp_avg_sq, eng.step] + list(eng.running_mean) + list(eng.running_var) + list(eng.nbt):
+                torch.distributed.broadcast(t, src=torch.distributed.get_global_rank(process_group, 0), group=process_group)
         self.x = torch.zeros(self.B, 3, 64, 64, device=dev)
         self.x_u8 = torch.zeros(self.B, 64, 64, 3, dtype=torch.uint8, device=dev)
         self.eps = torch.zeros(self.B, 32, device=dev)

@@ -24,6 +24,7 @@ from vae_parameters import *  # noqa: E402,F401,F403
 from vae_nets import *  # noqa: E402,F401,F403
 from vae_utility import *  # noqa: E402,F401,F403
 from cvae_native.trainer import TrainStep, shard_batch  # noqa: E402
+from cvae_native.loader import FrameStager  # noqa: E402
 
 
 def _dist():
@@ -38,15 +39,65 @@ def _dist():
     return dist.get_rank(), world, dist.group.WORLD
 
 
+def _as_u8_frames(frames_f32):
+    """float32 (N,3,64,64) frames that are exactly k/255 (MineRL povs after adjust_values, vae_utility.py:324-328)
+    back to uint8 HWC; None when they are not (e.g. the reconstruction dataset of -second)."""
+    u8 = np.rint(frames_f32 * 255.0)
+    if not np.array_equal(u8.astype(np.float32) / np.float32(255.0), frames_f32):
+        return None
+    return np.ascontiguousarray(u8.astype(np.uint8).transpose(0, 2, 3, 1))
+
+
+def _train_streamed(autoencoder, critic, frames_u8, logger, rank, world, pg):
+    """The same loop with the dataset in pinned host memory (uint8, 12 KB per frame) and double-buffered H2D staging
+    (cvae_native.loader.FrameStager) instead of an fp32 copy resident in HBM.  Chosen with CVAE_STREAM_FRAMES=1 or
+    when the fp32 dataset would not fit comfortably in device memory."""
+    pinned = torch.as_tensor(frames_u8).pin_memory()
+    num_samples = pinned.shape[0]
+    seed_rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little") if world == 1 else 0)
+    if world > 1:
+        torch.manual_seed(torch.initial_seed() + rank)      # per-rank reparameterisation noise
+    stagers = {}
+    for ep in range(epochs):
+        order = seed_rng.permutation(num_samples)
+        starts = list(range(0, num_samples, batch_size))
+        by_size = {}
+        for batch_i in starts:                               # the last, shorter batch is kept (vae.py:44-46)
+            idx = shard_batch(torch.as_tensor(order[batch_i:batch_i + batch_size]), rank, world)
+            if idx.numel():
+                by_size.setdefault(idx.numel(), []).append((batch_i, idx))
+        for B, items in by_size.items():
+            sg = stagers.get(B)
+            if sg is None:
+                sg = stagers[B] = FrameStager(TrainStep(autoencoder, critic, B, lr=lr, process_group=pg))
+            gather = (pinned.index_select(0, idx).pin_memory() for _, idx in items)
+            for (batch_i, _), losses in zip(items, sg.run(gather)):
+                if batch_i % log_n == 0 and rank == 0:
+                    print(f'    ep:{ep}, imgs:{num_samples * ep + (batch_i + 1)}', end='\r')
+                    if logger is not None:
+                        log_info({'total_loss': losses[0], 'recon_loss': losses[1], 'KLD': losses[2]}, logger, batch_i, ep, num_samples)
+                    autoencoder._engine.check_fault()
+    autoencoder._engine.check_fault()
+    return autoencoder
+
+
 def train(autoencoder, dset, logger=None, critic=None):
     """vae.py:33-66.  `dset`: list of (1,3,64,64) float32 frames (or an (N,3,64,64) array)."""
     critic = critic if critic is not None else globals().get("critic")
     rank, world, pg = _dist()
-    data = torch.as_tensor(np.stack(dset).squeeze().reshape(-1, ch, w, w), dtype=torch.float32).to(device)  # resident in HBM
-    num_samples = data.shape[0]
+    host = np.stack(dset).squeeze().reshape(-1, ch, w, w).astype(np.float32, copy=False)
     autoencoder.train()
+    free_bytes = torch.cuda.mem_get_info()[0] if torch.cuda.is_available() else 0
+    if os.environ.get("CVAE_STREAM_FRAMES") == "1" or host.nbytes > 0.4 * free_bytes:
+        u8 = _as_u8_frames(host)
+        if u8 is not None:
+            return _train_streamed(autoencoder, critic, u8, logger, rank, world, pg)
+    data = torch.as_tensor(host).to(device)                  # resident in HBM
+    num_samples = data.shape[0]
     steps = {}
     seed_rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little") if world == 1 else 0)
+    if world > 1:
+        torch.manual_seed(torch.initial_seed() + rank)       # per-rank reparameterisation noise (ranks share the data order only)
     losses = None
     for ep in range(epochs):
         order = torch.as_tensor(seed_rng.permutation(num_samples), device=data.device)
@@ -66,6 +117,7 @@ def train(autoencoder, dset, logger=None, critic=None):
                 print(f'    ep:{ep}, imgs:{num_samples * ep + (batch_i + 1)}', end='\r')
                 if logger is not None:
                     log_info({'total_loss': losses[0], 'recon_loss': losses[1], 'KLD': losses[2]}, logger, batch_i, ep, num_samples)
+                autoencoder._engine.check_fault()      # a device-side pipeline fault must not train on garbage until the end
     autoencoder._engine.check_fault()
     return autoencoder
 

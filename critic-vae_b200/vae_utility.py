@@ -210,6 +210,7 @@ def _score_episode(trajectory, vae, critic):
         d, m = _diff_grey(r_hi, r_lo)
         xs.append(x); preds.append(p); r1s.append(r_hi); r0s.append(r_lo); diffs.append(d); maxes.append(m)
     cat = lambda ts: torch.cat(ts) if ts else torch.empty(0, device=_dev())
+    vae._engine.check_fault()        # a device-side pipeline fault must never turn into silently wrong masks
     return cat(xs), cat(preds), cat(r1s), cat(r0s), cat(diffs), cat(maxes)
 
 
@@ -411,22 +412,36 @@ def load_minerl_data(critic, recon_dset=False, vae=None):
             break
         print(f'total images = {len(dset)}')
         povs = np.stack([o["pov"] for o, _, _, _, _ in data.load_data(name, skip_interval=0, include_metadata=False)])
-        x = frames_to_device(povs)
-        preds = critic.evaluate(x).reshape(-1)
-        picked = select_balanced(preds.cpu().tolist())
-        if not picked:
-            continue
-        idx = torch.tensor([i for i, _ in picked], device=x.device)
-        if recon_dset:
-            r_hi, r_lo = _recon_pair(vae, x[idx], preds[idx])
-            r_hi, r_lo = r_hi.cpu().numpy(), r_lo.cpu().numpy()
-            for j, (_, b) in enumerate(picked):
-                if b in ('mid', 'high'):
-                    dset.append(r_hi[j:j + 1])
-                if b in ('mid', 'low'):
-                    dset.append(r_lo[j:j + 1])
-        else:
-            sel = x[idx].cpu().numpy()
-            dset.extend(sel[j:j + 1] for j in range(sel.shape[0]))
+        dset.extend(dataset_from_trajectory(povs, critic, recon_dset=recon_dset, vae=vae))
     del data
     return dset
+
+
+def dataset_from_trajectory(povs, critic, recon_dset=False, vae=None):
+    """The per-trajectory body of load_minerl_data (vae_utility.py:416-457), batched: critic values of every frame in
+    one call (chunks of _CHUNK), the balanced mid / high / low selection on the host, then for the `-dataset` path
+    (recon_dset) the reconstructions with the critic value and with 0 of the selected frames in one batch.  Returns
+    the list of (1,3,64,64) float32 arrays the reference appends, in the reference's order."""
+    povs = np.asarray(povs)
+    x = torch.cat([frames_to_device(povs[s:s + _CHUNK]) for s in range(0, povs.shape[0], _CHUNK)]) if povs.shape[0] else None
+    if x is None:
+        return []
+    preds = torch.cat([critic.evaluate(x[s:s + _CHUNK]).reshape(-1) for s in range(0, x.shape[0], _CHUNK)])
+    picked = select_balanced(preds.cpu().tolist())
+    out = []
+    if not picked:
+        return out
+    idx = torch.tensor([i for i, _ in picked], device=x.device)
+    if recon_dset:
+        r_hi, r_lo = _recon_pair(vae, x[idx], preds[idx])
+        vae._engine.check_fault()
+        r_hi, r_lo = r_hi.cpu().numpy(), r_lo.cpu().numpy()
+        for j, (_, b) in enumerate(picked):
+            if b in ('mid', 'high'):
+                out.append(r_hi[j:j + 1])
+            if b in ('mid', 'low'):
+                out.append(r_lo[j:j + 1])
+    else:
+        sel = x[idx].cpu().numpy()
+        out.extend(sel[j:j + 1] for j in range(sel.shape[0]))
+    return out

@@ -136,8 +136,8 @@ def ssim_level(a, b, win):
 
 def msssim_loss(recon, x):
     """vae_nets.py:217-247: 1 - prod_{l<4}( cs_l^w_l * ssim_4^w_4 )."""
-    win = msssim_window_2d(recon.shape[1])
-    w = torch.tensor(MSSSIM_WEIGHTS, dtype=torch.float32)
+    win = msssim_window_2d(recon.shape[1]).to(recon.device)     # (device-agnostic: bench.py's gpu_baseline leg runs this on cuda)
+    w = torch.tensor(MSSSIM_WEIGHTS, dtype=torch.float32, device=recon.device)
     a, b = recon, x
     ss, cs = [], []
     for _ in range(5):
@@ -151,7 +151,7 @@ def msssim_loss(recon, x):
 
 def msssim_level_means(recon, x):
     """The ten batch-global means (ssim_l, cs_l) of vae_nets.py:224-236, for kernel-level checks."""
-    win = msssim_window_2d(recon.shape[1])
+    win = msssim_window_2d(recon.shape[1]).to(recon.device)
     a, b = recon, x
     out = []
     for _ in range(5):
