@@ -356,6 +356,9 @@ def run_b200(args):
     device = torch.device("cuda", local)
     pg = None
     if world > 1:
+        # one box, NVLink / NVSwitch only: never fall back to the host network
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")
         dist.init_process_group("nccl", device_id=device)
         pg = dist.group.WORLD
     B, R = args.batch, 4

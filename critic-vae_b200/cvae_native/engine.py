@@ -116,6 +116,7 @@ class VAEEngine:
         # data-gradient chain (fork / join with events, so the pair is CUDA-graph capturable).
         self.side_stream = None
         self.fold_stream = None     # third stream: split-K folds beside the next weight-gradient GEMM
+        self.early_event = None     # optional torch.cuda.Event(external=True) recorded when the early gradient bucket is final
 
     # ---- parameters ---------------------------------------------------------------------------
     def view(self, name, buf=None):
@@ -345,13 +346,48 @@ class VAEEngine:
             launch(L.stream_ptr())
         self._side_used = True
 
-    def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None, kld_grad_scale=0.0):
+    def _join_leaves(self):
+        """Wait (on the current stream) for the parameter-gradient launches that ran on the side / fold streams."""
+        if self._side_used:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+        if self._fold_used:
+            torch.cuda.current_stream().wait_stream(self.fold_stream)
+        self._side_used = self._fold_used = False
+
+    def early_bucket_offset(self):
+        """The flat gradient splits into [encoder convolutions + BatchNorm | everything else]: the second part (the two
+        Linear heads, the decoder, decoder_input: 58 % of the floats) is complete once the backward pass has walked the
+        decoder and the heads, long before the encoder's own gradients -- the data-parallel step all-reduces it beside them."""
+        return self.offsets["encoder.fc_mu.weight"][0]
+
+    def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None, kld_grad_scale=0.0, stage="all"):
         """Gradients of every parameter into the flat buffer `g` (default self.gflat), given the
-        gradients of the loss w.r.t. recon / mu / logvar.  Mirrors autograd through vae_nets.py:14-19."""
+        gradients of the loss w.r.t. recon / mu / logvar.  Mirrors autograd through vae_nets.py:14-19.
+        `stage`: "all", or "decoder" followed by "encoder" (two calls; after the first one the gradients from
+        early_bucket_offset() on are final)."""
         g = self.gflat if g is None else g
         B, s = ws.B, L.stream_ptr()
         G = lambda n: self.view(n, g)
-        self._side_used = self._fold_used = False
+        if stage != "encoder":
+            self._side_used = self._fold_used = False
+            self._backward_decoder(x, eps, ws, d_recon, d_mu, d_lv, g, kld_grad_scale)
+            if stage == "decoder":
+                self._join_leaves()
+                return g
+            if self.early_event is not None and self.side_stream is not None and self.profile is None:
+                # the gradients from early_bucket_offset() on are final once the side and fold streams reach this point:
+                # mark it with an event another stream (the data-parallel all-reduce) can wait on, also from outside a
+                # CUDA graph this call is captured into (external event record node)
+                if self._fold_used:
+                    self.side_stream.wait_stream(self.fold_stream)
+                self.early_event.record(self.side_stream)
+        self._backward_encoder(x, ws, g)
+        self._join_leaves()
+        return g
+
+    def _backward_decoder(self, x, eps, ws, d_recon, d_mu, d_lv, g, kld_grad_scale):
+        B, s = ws.B, L.stream_ptr()
+        G = lambda n: self.view(n, g)
         if self._bwd_packed is not None:
             torch.cuda.current_stream().wait_event(self._bwd_packed)
             self._bwd_packed = None
@@ -382,6 +418,10 @@ class VAEEngine:
                                                         _ptr(G("encoder.fc_mu.weight")), _ptr(G("encoder.fc_var.weight")),
                                                         _ptr(G("encoder.fc_mu.bias")), _ptr(G("encoder.fc_var.bias")), st)))
         L.check(L.lib.cvae_fc_bwd(B, _ptr(ws.dml), None, _ptr(self.packed["fc"]), _ptr(ws.g_a[3]), None, None, None, None, s))
+
+    def _backward_encoder(self, x, ws, g):
+        B, s = ws.B, L.stream_ptr()
+        G = lambda n: self.view(n, g)
         em = "encoder.model."
         for i in (3, 2, 1, 0):
             ci, co, h = ENC[i]
@@ -396,11 +436,6 @@ class VAEEngine:
                 self._wgrad(g, cname, kind=L.WGRAD_5X5, batch=B, height=h, width=h, cout=co, cin=ci, x=ws.a[i - 1], dy=ws.g_c[i])
                 self._conv(f"E{i}g", batch=B, height=h, width=h, ksize=5, src_channels=co, n_total=ci, loader=L.LOAD_NHWC,
                            epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
-        if self._side_used:
-            torch.cuda.current_stream().wait_stream(self.side_stream)
-        if self._fold_used:
-            torch.cuda.current_stream().wait_stream(self.fold_stream)
-        return g
 
     # ---- optimizer ----------------------------------------------------------------------------
     def adam_step(self, lr, grad_scale=1.0, betas=(0.9, 0.999), eps=1e-8, g=None):

@@ -3,10 +3,12 @@
     preds = critic.evaluate(images); opt.zero_grad(); out = autoencoder(images, preds)
     losses = autoencoder.vae_loss(*out); losses['total_loss'].backward(); opt.step()
 
-as ONE replayable CUDA graph per batch size (about 75 kernel launches, no host work in between),
-with an optional NCCL gradient all-reduce between backward and Adam for data-parallel training
-(one process per GPU, PyTorch-DDP semantics: per-rank loss/grads on the local shard, Adam on the
-mean gradient; BatchNorm statistics stay per-rank).
+as ONE replayable CUDA graph per batch size (about 75 kernel launches, no host work in between).
+Data-parallel training (one process per GPU, PyTorch-DDP semantics: per-rank loss/grads on the local
+shard, Adam on the mean gradient; BatchNorm statistics stay per-rank) all-reduces the
+gradient over NCCL in two buckets between a forward/backward graph and an Adam graph; the first bucket
+(decoder + heads) starts beside the encoder's backward pass, triggered by an external event node inside
+the graph.
 
 torch supplies device memory, streams, graph capture and the process group; all arithmetic is in
 libcvae.so.
@@ -60,9 +62,15 @@ class TrainStep:
             self.eng.fold_stream = torch.cuda.Stream()
         self._use_graph = use_graph
         self.launches_per_step = None
+        # data parallel: all-reduce the early gradient bucket beside the encoder's backward pass (CVAE_DP_OVERLAP=0: one
+        # all-reduce of the whole gradient after the pass, the round-1 scheme)
+        self.overlap = self.world > 1 and self.eng.side_stream is not None and os.environ.get("CVAE_DP_OVERLAP", "1") != "0"
+        if self.overlap:
+            self.comm_stream = torch.cuda.Stream()
+            self.early_event = torch.cuda.Event(external=True)
 
     # ---- the work ---------------------------------------------------------------------------------
-    def _front(self, from_u8):
+    def _front(self, from_u8, stage="all"):
         eng, ws, s = self.eng, self.ws, L.stream_ptr()
         if from_u8:
             L.check(L.lib.cvae_frames_u8_to_f32(self.B, self.x_u8.data_ptr(), self.x.data_ptr(), s))
@@ -86,15 +94,39 @@ class TrainStep:
         # the KL term rides along with the latent kernels: partial sums in the forward, its gradient in the backward
         eng.loss_forward(ws.recon, self.x, ws.ml, ws, fused_kld=True)
         eng.loss_backward(ws.recon, self.x, ws.ml, ws, fused_kld=True)
-        eng.backward(self.x, self.eps, ws, ws.d_recon, None, None, kld_grad_scale=KLD_WEIGHT / self.B)
+        eng.early_event = self.early_event if self.overlap else None      # (the engine is shared between TrainSteps)
+        eng.backward(self.x, self.eps, ws, ws.d_recon, None, None, kld_grad_scale=KLD_WEIGHT / self.B, stage=stage)
+        eng.early_event = None
+
+    def _front_encoder(self):
+        self.eng.backward(self.x, self.eps, self.ws, self.ws.d_recon, None, None, stage="encoder")
 
     def _back(self):
         self.eng.adam_step(self.lr, grad_scale=1.0 / self.world)
 
+    def _buckets(self):
+        """(early, late) views of the flat gradient: see VAEEngine.early_bucket_offset."""
+        off = self.eng.early_bucket_offset()
+        return self.eng.gflat[off:], self.eng.gflat[:off]
+
+    def _allreduce(self):
+        """Sum the flat gradient over the ranks, after _front has been launched on the current stream: the early bucket
+        on the communication stream as soon as the event inside the backward pass fires (beside the encoder's backward
+        pass), the late bucket behind the whole pass; the current stream then waits for both."""
+        early, late = self._buckets()
+        if self.overlap:
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(self.early_event)
+                w1 = torch.distributed.all_reduce(early, group=self.pg, async_op=True)
+            w2 = torch.distributed.all_reduce(late, group=self.pg, async_op=True)
+            w1.wait(); w2.wait()
+        else:
+            torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
+
     def _eager(self, from_u8):
         self._front(from_u8)
         if self.world > 1:
-            torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
+            self._allreduce()
         self._back()
 
     def _capture(self, from_u8):
@@ -115,20 +147,20 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         eng.check_fault()
-        # Single GPU: one graph for the whole step.  Data parallel: the NCCL all-reduce stays OUTSIDE graph capture,
-        # between a forward/backward graph and an Adam graph (capturing the collective hung an 8-rank run on this
-        # pool; CVAE_CAPTURE_ALLREDUCE=1 opts back in, CVAE_SPLIT_GRAPH=1 forces the split on one GPU too).
-        single = (self.world == 1 and os.environ.get("CVAE_SPLIT_GRAPH") is None) or \
-                 (self.world > 1 and os.environ.get("CVAE_CAPTURE_ALLREDUCE") is not None)
-        if single:
-            g_front, g_back = torch.cuda.CUDAGraph(), None
-            with torch.cuda.graph(g_front):
+        # Single GPU: one graph for the whole step.  Data parallel: a forward/backward graph and an Adam graph with the
+        # NCCL all-reduces issued from the host between them (capturing the collectives inside the graph hung an 8-rank
+        # run on this pool in round 1).  The forward/backward graph carries an EXTERNAL event record node at the point
+        # where the early gradient bucket (decoder + heads, 58 % of the floats) is final, so its all-reduce starts on the
+        # communication stream while the graph is still walking the encoder's backward pass.
+        if self.world == 1:
+            graphs = [torch.cuda.CUDAGraph()]
+            with torch.cuda.graph(graphs[0]):
                 self._eager(from_u8)
         else:
-            g_front, g_back = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_front):
+            graphs = [torch.cuda.CUDAGraph() for _ in range(2)]
+            with torch.cuda.graph(graphs[0]):
                 self._front(from_u8)
-            with torch.cuda.graph(g_back):
+            with torch.cuda.graph(graphs[1]):
                 self._back()
         # undo the warm-up step
         eng.flat.copy_(keep[0]); eng.step.copy_(keep[1])
@@ -139,7 +171,7 @@ class TrainStep:
             eng.exp_avg.copy_(keep_m); eng.exp_avg_sq.copy_(keep_v)
         else:
             eng.exp_avg.zero_(); eng.exp_avg_sq.zero_()
-        return g_front, g_back
+        return graphs
 
     # ---- public -----------------------------------------------------------------------------------
     def load(self, frames=None, eps=None, frames_u8=None, non_blocking=True):
@@ -163,8 +195,7 @@ class TrainStep:
         if gs is None:
             gs = self._graphs[from_u8] = self._capture(from_u8)
         gs[0].replay()
-        if gs[1] is not None:
-            if self.world > 1:
-                torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
+        if self.world > 1:
+            self._allreduce()
             gs[1].replay()
         return self.losses

@@ -35,6 +35,8 @@ def _dist():
     import torch.distributed as dist
     if not dist.is_initialized():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")      # one box, NVLink / NVSwitch only
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")
         dist.init_process_group("nccl")
     return dist.get_rank(), world, dist.group.WORLD
 
