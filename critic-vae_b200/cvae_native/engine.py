@@ -51,6 +51,27 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_NVTX = os.environ.get("CVAE_NVTX") == "1"
+
+
+def _nvtx(name):
+    """NVTX range around a phase of the step (encode / decode / loss / backward / adam) for nsys / ncu timelines
+    (SURVEY.md section 5).  Off unless CVAE_NVTX=1: the push/pop pair costs host time on the eager path."""
+    def deco(fn):
+        if not _NVTX:
+            return fn
+
+        def wrapped(*a, **kw):
+            torch.cuda.nvtx.range_push("cvae." + name)
+            try:
+                return fn(*a, **kw)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        wrapped.__doc__ = fn.__doc__
+        return wrapped
+    return deco
+
+
 class Workspace:
     """Activation / gradient buffers for one batch size."""
 
@@ -238,6 +259,7 @@ class VAEEngine:
                 d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
         self._timed("conv_gemm", lambda: L.check(L.lib.cvae_conv_gemm(ctypes.byref(d), L.stream_ptr())))
 
+    @_nvtx("encode")
     def encode(self, x, training, ws, pack=True):
         """x fp32 NCHW [B,3,64,64] -> ws.ml = mu | logvar.  vae_nets.py:101-111."""
         B, s = ws.B, L.stream_ptr()
@@ -269,6 +291,7 @@ class VAEEngine:
                                   _ptr(self.view("encoder.fc_var.bias")), _ptr(ws.ml), s))
         return ws.ml
 
+    @_nvtx("decode")
     def decode(self, pred, eps, sample, ws, pack=False):
         """ws.ml, pred fp32 [B] (+ eps fp32 [B,32]) -> ws.recon fp32 NCHW.  vae_nets.py:48-51,139-147."""
         B, s = ws.B, L.stream_ptr()
@@ -292,6 +315,7 @@ class VAEEngine:
         return ws.recon
 
     # ---- loss ---------------------------------------------------------------------------------
+    @_nvtx("loss_forward")
     def loss_forward(self, recon, x, ml, ws, kld_weight=KLD_WEIGHT, fused_kld=False):
         """`fused_kld`: ml is ws.ml of the decode() that just ran with sample=True, so the KL partial sums the latent
         kernel left in ws.kld_partial are used instead of re-reading mu / logvar (TrainStep)."""
@@ -299,6 +323,7 @@ class VAEEngine:
                                     kld_weight, _ptr(ws.loss_sums), _ptr(ws.coef), _ptr(ws.losses), L.stream_ptr()))
         return ws.losses
 
+    @_nvtx("loss_backward")
     def loss_backward(self, recon, x, ml, ws, grad_out=None, kld_weight=KLD_WEIGHT, fused_kld=False):
         """`fused_kld`: skip the KL term's backward here; backward(..., kld_grad_scale=kld_weight / B) adds it inside the
         latent backward kernel (only valid with grad_out None, i.e. an upstream gradient of 1)."""
@@ -360,6 +385,7 @@ class VAEEngine:
         decoder and the heads, long before the encoder's own gradients -- the data-parallel step all-reduces it beside them."""
         return self.offsets["encoder.fc_mu.weight"][0]
 
+    @_nvtx("backward")
     def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None, kld_grad_scale=0.0, stage="all"):
         """Gradients of every parameter into the flat buffer `g` (default self.gflat), given the
         gradients of the loss w.r.t. recon / mu / logvar.  Mirrors autograd through vae_nets.py:14-19.
@@ -438,6 +464,7 @@ class VAEEngine:
                            epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
 
     # ---- optimizer ----------------------------------------------------------------------------
+    @_nvtx("adam")
     def adam_step(self, lr, grad_scale=1.0, betas=(0.9, 0.999), eps=1e-8, g=None):
         if self.exp_avg is None:
             self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
@@ -445,6 +472,7 @@ class VAEEngine:
         L.check(L.lib.cvae_adam_step(self.n_params, _ptr(self.flat), _ptr(g), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
                                      _ptr(self.step), lr, betas[0], betas[1], eps, grad_scale, L.stream_ptr()))
 
+    @_nvtx("critic")
     def critic(self, x, weights, out=None):
         N = x.shape[0]
         out = torch.empty(N, 1, device=self.device) if out is None else out
