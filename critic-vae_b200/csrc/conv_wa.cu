@@ -62,6 +62,7 @@ struct WaArgs {
     int unit_bytes, ups, nstages, stage_bytes;  // weight ring: units per stage
     int phase_src;                // 1: block q comes from tensor map q (space-to-depth phases), channel 0
     int w_tma;                    // weight stages through a 2-D tensor map (one box per unit) instead of 1-D bulk copies
+    int dbg_flags;                // experiments (CVAE_WA_DBG): 1 skip TMEM loads, 2 skip the transpose, 4 skip the stores
     int epilogue;
     int goff[kWaMaxGroups];       // B operand start of every tap group, in 16-byte descriptor units from the slot base:
                                   // (margin + pad * PW - (J - 1) + dy * PW + s) * row_bytes / 16
@@ -82,6 +83,11 @@ struct WaBars {
     uint64_t acc_full[2], acc_empty[2];
 };
 
+__device__ __forceinline__ unsigned long long wa_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -186,9 +192,9 @@ __device__ __forceinline__ void wa_emit8(const WaArgs& a, float (&v)[8], int nva
             }
         }
     }
-    transpose8x8_bf16(R, lane);
+    if (!(a.dbg_flags & 2)) transpose8x8_bf16(R, lane);
     const int j = lane & 7, cg = cbase + (lane >> 3) * 8;
-    if (j < nvalid && lane_live) {
+    if (j < nvalid && lane_live && !(a.dbg_flags & 4)) {
         const int pix = pix0 + j;
         size_t off;
         if constexpr (EPI == CVAE_EPI_PHASE_BIAS_RELU) {
@@ -228,7 +234,10 @@ __device__ __forceinline__ void wa_batch(const WaArgs& a, const WaGroup (&g)[NB]
     if constexpr (!FROM_WS) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            if (b < count) {
+            if (a.dbg_flags & 1) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) raw[b][i] = 0x3f800000u;
+            } else if (b < count) {
                 if constexpr (J > 1) {
                     tmem_ld16(tbase + (uint32_t)g[b].col, raw[b]);
                 } else if (g[b].col2 == -2) {          // W >= 8: eight columns of one row
@@ -338,6 +347,7 @@ conv_wa_kernel(const WaArgs a, const __grid_constant__ CUtensorMap map0, const _
     __shared__ int last_flag;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 16 + 8] = wa_now_ns();     // phase timestamps (profiling aid): kernel entry
     uint8_t* const bring = smem;                                       // [nslots][slot_bytes]
     uint8_t* const wring = smem + (size_t)a.nslots * a.slot_bytes;     // [nstages][stage_bytes]
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
@@ -359,6 +369,7 @@ conv_wa_kernel(const WaArgs a, const __grid_constant__ CUtensorMap map0, const _
     tc_fence_before();
     if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
+    if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 16 + 9] = wa_now_ns();     // prologue done
     const uint32_t tmem_base = tmem_slot;
     const int items = a.nt * a.m_blocks;
     const int G = gridDim.x / a.ksplit, ks = blockIdx.x / G;           // tile group count, this CTA's K slice
@@ -422,7 +433,8 @@ conv_wa_kernel(const WaArgs a, const __grid_constant__ CUtensorMap map0, const _
             s2[mb & 1] += t2;
             t_epi += clock64() - te;
         }
-        if (a.dbg && tid == 0) { a.dbg[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)t_epi; a.dbg[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)t_red; }
+        if (a.dbg && tid == 0) { a.dbg[(size_t)blockIdx.x * 16 + 6] = (unsigned long long)t_epi; a.dbg[(size_t)blockIdx.x * 16 + 7] = (unsigned long long)t_red; }
+        if (a.dbg && lane == 0) atomicMax(a.dbg + (size_t)blockIdx.x * 16 + 12, wa_now_ns());    // last epilogue warp done
         if constexpr (EPI == CVAE_EPI_STATS) {
             if (J == 1 || lane < 32 / J) {
                 for (int mb = 0; mb < a.m_blocks; ++mb) {
@@ -548,6 +560,7 @@ conv_wa_kernel(const WaArgs a, const __grid_constant__ CUtensorMap map0, const _
                         }
                         const uint32_t a_lo = (wring16 + wslot * stage16 + (uint32_t)uin * unit16) | a_lbo;
                         const uint32_t b_lo = (b_slot16 + (uint32_t)goff) | b_lbo;
+                        if (prof && it == 0 && u == 0) a.dbg[(size_t)blockIdx.x * 16 + 10] = wa_now_ns();   // first MMA
                         if (a.kb == 64) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
@@ -572,10 +585,11 @@ conv_wa_kernel(const WaArgs a, const __grid_constant__ CUtensorMap map0, const _
                 umma_commit(&bars.acc_full[ab]);
             }
             if (prof) {
-                unsigned long long* o = a.dbg + (size_t)blockIdx.x * 8;
+                unsigned long long* o = a.dbg + (size_t)blockIdx.x * 16;
                 unsigned long long g1;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
                 o[0] = (unsigned long long)(clock64() - t0); o[1] = t_acc; o[2] = t_b; o[3] = t_w; o[4] = items; o[5] = g1 - g0;
+                o[11] = g1;                                                                         // last MMA issued
             }
         }
         __syncwarp();
@@ -583,6 +597,7 @@ conv_wa_kernel(const WaArgs a, const __grid_constant__ CUtensorMap map0, const _
     tc_fence_before();
     if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 0) tmem_free(tmem_base, 512);
+    if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 16 + 13] = wa_now_ns();    // kernel exit
 }
 
 static const bool g_wa_debug = getenv("CVAE_DEBUG") != nullptr;
@@ -709,20 +724,23 @@ static int wa_plan(const cvae_conv_desc* d, WaPlan& p) {
     const int row_bytes = a.kb * 2;
     const int slot_rows = kWaMarginLo + (tile_rows + 2 * a.pad) * a.PW + 16 + a.pad + J + 8;
     a.slot_bytes = (slot_rows * row_bytes + 1023) & ~1023;
-    const size_t cap = 214 * 1024;
+    const size_t cap = 224 * 1024;                       // 227 KB per CTA minus the static shared memory (barriers)
     const int nblk_s = a.nblk / ksplit;
-    a.nslots = nblk_s >= 3 ? 3 : 2;
-    a.ups = g_wa_ups > 0 ? g_wa_ups : (32768 / a.unit_bytes);   // ~32 KB stages: the MMA thread pays a fixed cost per stage
-    for (;;) {
+    a.nslots = 2;
+    // Weight stages as large as still leaves three of them in flight: the MMA thread pays ~900 cycles per stage for its
+    // barrier wait, fence and commit whatever the stage holds (tools/umma_rate.cu wa: 8 MMAs per stage run at
+    // max(900, MMA time + 220) cycles), so an N = 176 tile needs >= 12 MMAs per stage to stay bound by the tensor pipe.
+    const int per16k = 16384 / a.unit_bytes;              // units per 16 KB (1 for 64-channel blocks, 2 for 32-channel blocks)
+    for (int u16 : {4, 3, 2, 1}) {
+        a.ups = g_wa_ups > 0 ? g_wa_ups : u16 * per16k;
         a.stage_bytes = a.ups * a.unit_bytes;
         const long left = (long)cap - (long)a.nslots * a.slot_bytes;
-        a.nstages = (int)(left / a.stage_bytes);
-        if (a.nstages >= 3 || a.ups == 1) break;
-        a.ups = (a.ups + 1) / 2;
+        a.nstages = left > 0 ? (int)(left / a.stage_bytes) : 0;
+        if (a.nstages >= 3 || g_wa_ups > 0) break;
     }
     if (a.nstages > kWaMaxStages) a.nstages = kWaMaxStages;
     CVAE_REQUIRE(a.nstages >= 2, CVAE_EINVAL, "conv_wa: shape does not fit shared memory");
-    // spend what is left on more pixel slots (deeper prefetch across tiles)
+    // spend what is left on more pixel slots (deeper prefetch across blocks and tiles)
     while (a.nslots < kWaMaxSlots && a.nslots < 2 * nblk_s &&
            (size_t)(a.nslots + 1) * a.slot_bytes + (size_t)a.nstages * a.stage_bytes <= cap) ++a.nslots;
     p.smem = (size_t)a.nslots * a.slot_bytes + (size_t)a.nstages * a.stage_bytes;
@@ -776,6 +794,8 @@ int conv_wa_dispatch(const cvae_conv_desc* d, cudaStream_t stream) {
         }
     }
     a.w_tma = g_wa_wload == 2 ? 1 : 0;
+    static const int dbg_flags = getenv("CVAE_WA_DBG") ? atoi(getenv("CVAE_WA_DBG")) : 0;
+    a.dbg_flags = dbg_flags;
     ok = ok && encode_map_2d(&maps[4], d->wpack, 64, (long)a.m_blocks * a.nblk * a.upb * (a.unit_bytes >> 7), 64, a.unit_bytes >> 7);
     CVAE_REQUIRE(ok, CVAE_ECUDA, "conv_wa: cuTensorMapEncodeTiled failed");
     if (g_wa_debug)

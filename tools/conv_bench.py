@@ -106,14 +106,18 @@ def bench(name, H, k, C, N, loader, epi, tm=0, nblk=0, iters=20):
     torch.cuda.synchronize()
     us = a.elapsed_time(b) * 1e3 / iters
     if os.environ.get("CVAE_COUNTERS") and wa:
-        buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+        buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
         L.lib.cvae_conv_wa_debug_counters(buf.data_ptr())
         L.lib.cvae_conv_gemm(ctypes.byref(d), s)
         torch.cuda.synchronize()
         L.lib.cvae_conv_wa_debug_counters(None)
-        c = buf.view(148, 8).cpu().double()
+        c = buf.view(148, 16).cpu().double()
         c = c[c[:, 0] > 0]
         m = c.mean(0)
+        t0 = c[:, 8].min()
+        ph = lambda k: (c[:, k] - t0).mean().item() * 1e-3
+        print(f"   {name} [wa phases, us from first CTA start, mean over CTAs] entry {ph(8):.1f}  prologue done {ph(9):.1f}  first MMA {ph(10):.1f}  "
+              f"last MMA issued {ph(11):.1f}  epilogue done {ph(12):.1f}  exit {ph(13):.1f} (last CTA exit {(c[:, 13].max() - t0) * 1e-3:.1f})")
         print(f"   {name} [wa] ctas={c.shape[0]} MMA thread: total {m[0]:.0f} cyc (max {c[:, 0].max():.0f}), wait acc {m[1]:.0f}, pixels {m[2]:.0f}, "
               f"weights {m[3]:.0f}, items {m[4]:.1f}, SM clock {m[0] / max(m[5], 1) * 1e3:.0f} MHz | epilogue {m[6]:.0f} (split-K reduce max {c[:, 7].max():.0f})")
     elif os.environ.get("CVAE_COUNTERS"):

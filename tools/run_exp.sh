@@ -1,10 +1,2 @@
-for OV in 1 0; do
-echo "--- bench 8 overlap=$OV"; CVAE_DP_OVERLAP=$OV timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2952$OV bench.py --gpus 8 --steps 200 --warmup 5 --no-secondary 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, 'e2e', d['e2e']['value'])"
-done
-echo "--- cfg4 at 8"; timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29525 bench.py --gpus 8 --steps 50 --warmup 5 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, 'cfg4', d.get('cfg4'))"
+timeout 600 python -m pytest tests/test_conv_gemm.py -q -x -k "wa_" 2>&1 | grep -E "^FAILED|^E  |passed|failed" | cut -c1-200 | head
+echo "--- default"; CVAE_DEBUG=1 CVAE_COUNTERS=1 CVAE_WA_ONLY=E2f,E3f,E3g,E2g,D0f,D2f,D2g,D1g,D0g timeout 200 python tools/conv_bench.py 256 --wa 2>&1 | grep -E "^conv_wa E|wa\]|^[A-Z][0-9][fg]:|sum"

@@ -405,7 +405,109 @@ static void run_mn(const char* name, RateArgs p, int grid) {
     cudaFree(d);
 }
 
+// The weights-as-A pattern of conv_wa.cu: A = no-swizzle K-major 128 x 64 units (16 KB: four K = 16 steps 4 KB apart) in a
+// ring, B = one SWIZZLE_128B K-major pixel tile read at 25 tap-shifted (not 8-row aligned) starts, 32 B per K step.
+// mode bit 0: a second warp keeps streaming 16 KB bulk copies global -> the A ring (what the weight producer does).
+__global__ void __launch_bounds__(128, 1) wa_kernel(RateArgs p, const uint8_t* gsrc, uint32_t mode, uint32_t pw) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar, cbar[4], done_bar, sink_bar[8];
+    __shared__ uint32_t tmem_slot;
+    __shared__ volatile int stop;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (uint32_t i = tid * 16; i < 200 * 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init(&done_bar, 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&sink_bar[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&cbar[i], 1);
+        mbar_fence_init();
+        mbar_arrive(&done_bar);
+        stop = 0;
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_bf16(p.n, kMajorK, kMajorK);
+            const uint32_t a16 = (smem_u32(smem) & 0x3FFFFu) >> 4, b16 = ((smem_u32(smem) + 128 * 1024) & 0x3FFFFu) >> 4;
+            const uint32_t a_hi = (256u >> 4) | (1u << 14), a_lbo = (128u >> 4) << 16;
+            const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29), b_lbo = 1u << 16;
+            const long long t0 = clock64();
+            uint32_t unit = 0;
+            for (uint32_t r = 0; r < p.reps; r += 4, ++unit) {
+                const uint32_t tap = unit % 25u, ty = tap / 5u, tx = tap - ty * 5u;
+                const uint32_t a_lo = (a16 + (unit & 7u) * 1024u) | a_lbo;
+                const uint32_t b_lo = (b16 + (8u + ty * pw + tx) * 8u) | b_lbo;
+                if ((unit & 1u) == 0) {      // what conv_wa's MMA thread does once per weight stage (two units)
+                    if (mode & 8u) mbar_wait(&done_bar, 0, &g_rate_fault);       // a barrier that completed long ago
+                    if (mode & 4u) tc_fence_after();
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    umma_bf16(tmem_base, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(j * 256)),
+                              ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(j * 2)), idesc, 1u);
+                if ((unit & 1u) && (mode & 2u)) umma_commit(&sink_bar[(unit >> 1) & 7u]);
+            }
+            umma_commit(&bar);
+            mbar_wait(&bar, 0, &g_rate_fault);
+            p.out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+            stop = 1;
+        }
+        __syncwarp();
+    } else if (warp == 1 && (mode & 1u)) {
+        if (elect_one()) {
+            uint32_t i = 0;
+            while (!stop) {
+                const uint32_t s = i & 3u;
+                if (i >= 4) mbar_wait(&cbar[s], ((i >> 2) - 1) & 1u, &g_rate_fault);
+                mbar_expect_tx(&cbar[s], 16384);
+                bulk_g2s(smem + (size_t)(i & 7u) * 16384, gsrc + (size_t)((i * 16384u) & ((1u << 20) - 1)), 16384, &cbar[s]);
+                ++i;
+            }
+            for (uint32_t k = (i > 4 ? i - 4 : 0); k < i; ++k) mbar_wait(&cbar[k & 3u], (k >> 2) & 1u, &g_rate_fault);
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem_base, 512);
+}
+static void run_wa(uint32_t n, int grid, uint32_t mode, uint32_t pw, const uint8_t* gsrc) {
+    unsigned long long* d;
+    cudaMalloc(&d, grid * 8);
+    cudaMemset(d, 0, grid * 8);
+    RateArgs p{};
+    p.n = n; p.reps = 1600; p.out = d;
+    cudaFuncSetAttribute(wa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    wa_kernel<<<grid, 128, 200 * 1024>>>(p, gsrc, mode, pw);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("wa ERROR %s\n", cudaGetErrorString(e)); exit(1); }
+    unsigned long long h[148];
+    cudaMemcpy(h, d, grid * 8, cudaMemcpyDeviceToHost);
+    double sum = 0;
+    for (int i = 0; i < grid; ++i) sum += (double)h[i];
+    printf("WA pattern N=%3u grid=%3d weights %-30s per stage:%s%s%s : %7.1f cycles/MMA (N/2 = %u)\n", n, grid,
+           (mode & 1) ? "streaming (16 KB bulk copies)" : "resident", (mode & 8) ? " try_wait" : "", (mode & 4) ? " fence" : "",
+           (mode & 2) ? " commit" : "", sum / grid / p.reps, n / 2);
+    cudaFree(d);
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "wa")) {
+        uint8_t* gsrc;
+        cudaMalloc(&gsrc, 2 << 20);
+        cudaMemset(gsrc, 0, 2 << 20);
+        for (int grid : {1, 148})
+            for (uint32_t mode : {0u, 1u})
+                for (uint32_t n : {144u, 176u, 208u, 256u}) run_wa(n, grid, mode, 18, gsrc);
+        for (uint32_t mode : {2u, 4u, 8u, 14u, 15u})
+            for (uint32_t n : {64u, 144u, 176u}) run_wa(n, 148, mode, 18, gsrc);
+        return 0;
+    }
     const uint32_t reps = 960;
     if (argc > 1 && !strcmp(argv[1], "real")) {
         // mode bit 0: three warps hammer shared memory with st.shared.v4; bit 1: one warp streams 8 KB bulk copies
