@@ -200,27 +200,40 @@ class VAEEngine:
         self._jobs = (L.PackJob * len(jobs))(*jobs)
         # data-gradient forms (keys ending in "g") are first needed by the backward pass
         keys = list(self.packed.keys())
-        fwd = [j for j, k in zip(jobs, keys) if not k.endswith("g")]
+        # with a side stream only encoder conv 0's 13 KB form is packed in front of the forward pass; the other forward
+        # forms are packed beside conv 0 / its BatchNorm, the data-gradient forms beside the rest of the forward pass
+        first = [j for j, k in zip(jobs, keys) if k == "E0f"]
+        fwd = [j for j, k in zip(jobs, keys) if not k.endswith("g") and k != "E0f"]
         bwd = [j for j, k in zip(jobs, keys) if k.endswith("g")]
+        self._jobs_first = (L.PackJob * len(first))(*first)
         self._jobs_fwd = (L.PackJob * len(fwd))(*fwd)
         self._jobs_bwd = (L.PackJob * len(bwd))(*bwd)
-        self._bwd_packed = None
+        self._bwd_packed = self._fwd_packed = None
 
     def pack(self):
-        """Repack every operand form from the fp32 masters.  With a side stream the data-gradient forms are
-        packed beside the forward pass; backward() waits for them."""
+        """Repack every operand form from the fp32 masters.  With a side stream only encoder conv 0's form is packed on
+        the calling stream; encode() waits for the other forward forms before encoder conv 1, backward() for the
+        data-gradient forms."""
         if self.side_stream is None:
             L.check(L.lib.cvae_pack_weights(self._jobs, len(self._jobs), L.stream_ptr()))
-            self._bwd_packed = None
+            self._bwd_packed = self._fwd_packed = None
             return
         fork = torch.cuda.Event()
         fork.record()
         self.side_stream.wait_event(fork)
         with torch.cuda.stream(self.side_stream):
+            L.check(L.lib.cvae_pack_weights(self._jobs_fwd, len(self._jobs_fwd), L.stream_ptr()))
+            self._fwd_packed = torch.cuda.Event()
+            self._fwd_packed.record()
             L.check(L.lib.cvae_pack_weights(self._jobs_bwd, len(self._jobs_bwd), L.stream_ptr()))
             self._bwd_packed = torch.cuda.Event()
             self._bwd_packed.record()
-        L.check(L.lib.cvae_pack_weights(self._jobs_fwd, len(self._jobs_fwd), L.stream_ptr()))
+        L.check(L.lib.cvae_pack_weights(self._jobs_first, len(self._jobs_first), L.stream_ptr()))
+
+    def _await_fwd_pack(self):
+        if self._fwd_packed is not None:
+            torch.cuda.current_stream().wait_event(self._fwd_packed)
+            self._fwd_packed = None
 
     def workspace(self, B, with_grad):
         key = (B, with_grad)
@@ -275,6 +288,7 @@ class VAEEngine:
                 self._conv(batch=B, height=h, width=h, ksize=5, src_channels=8, n_total=co, loader=L.LOAD_NCHW3,
                            epilogue=L.EPI_STATS, ktab=L.KTAB_PAIR8, src=x, wpack=self.packed["E0f"], out=ws.c[0], stats=stats)
             else:
+                self._await_fwd_pack()
                 self._conv(f"E{i}f", batch=B, height=h, width=h, ksize=5, src_channels=ci, n_total=co, loader=L.LOAD_NHWC,
                            epilogue=L.EPI_STATS, ktab=L.KTAB_GENERIC, src=ws.a[i - 1], wpack=self.packed[f"E{i}f"],
                            out=ws.c[i], stats=stats)
@@ -297,6 +311,7 @@ class VAEEngine:
         B, s = ws.B, L.stream_ptr()
         if pack:
             self.pack()
+        self._await_fwd_pack()       # (a decode() that packs itself, e.g. Decoder.forward: "fc" / "decin" are forward forms)
         # fused reparametrise + critic concat + KL partial sums (consumed by loss_forward when it is given ws.ml itself)
         L.check(L.lib.cvae_latent_fwd(B, int(sample), _ptr(ws.ml), _ptr(eps), _ptr(pred), _ptr(ws.zc),
                                       _ptr(ws.kld_partial) if sample else None, s))

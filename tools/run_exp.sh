@@ -1,2 +1,9 @@
-timeout 600 python -m pytest tests/test_conv_gemm.py -q -x -k "wa_" 2>&1 | grep -E "^FAILED|^E  |passed|failed" | cut -c1-200 | head
-echo "--- default"; CVAE_DEBUG=1 CVAE_COUNTERS=1 CVAE_WA_ONLY=E2f,E3f,E3g,E2g,D0f,D2f,D2g,D1g,D0g timeout 200 python tools/conv_bench.py 256 --wa 2>&1 | grep -E "^conv_wa E|wa\]|^[A-Z][0-9][fg]:|sum"
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
+echo "--- bench"; timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/r02_bench_c.json 2> gpurun_out/r02_bench_c.err; tail -3 gpurun_out/r02_bench_c.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02_bench_c.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','clocks')})
+print('e2e', d['e2e']['value'], 'roofline', d['roofline']['frac'], d['roofline']['traffic'], d['roofline']['families'])
+g=d.get('gpu_baseline',{}); print('gpu_baseline', {k:(v.get('ms_per_step') or v.get('error')) for k,v in g.get('variants',{}).items()}, g.get('speedup_vs_best_stock_pytorch'))
+print('dataset', d.get('dataset_path',{}).get('frames_per_s')); print('latent', d.get('latent_kernel',{}).get('frac')); print('mask', d.get('mask_iou',{}).get('frac'))
+PY
