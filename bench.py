@@ -287,23 +287,25 @@ def gpu_baseline(device, batch, steps=20, warmup=5):
             for graphed in (False, True):
                 name = f"{mode}_{'graph' if graphed else 'eager'}"
                 try:
-                    step = make_step(mode)
+                    # parameters, warm-up and capture all live on ONE side stream: autograd's AccumulateGrad nodes run on the
+                    # stream their leaf was created on, and a node on the default stream invalidates the capture
                     side = torch.cuda.Stream()
                     side.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(side):
+                        step = make_step(mode)
                         for _ in range(warmup):
                             loss = step()
-                    torch.cuda.current_stream().wait_stream(side)
-                    torch.cuda.synchronize()
-                    fn = step
-                    if graphed:
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g):
-                            loss = step()
-                        fn = g.replay
-                        fn()
-                    ms = timed(fn, steps)
-                    out["variants"][name] = {"ms_per_step": ms, "frames_per_s": batch / (ms * 1e-3), "loss": float(loss)}
+                        fn = step
+                        if graphed:
+                            side.synchronize()
+                            g = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(g, stream=side):
+                                loss = step()
+                            fn = g.replay
+                            fn()
+                        side.synchronize()
+                        ms = timed(fn, steps)
+                    out["variants"][name] = {"ms_per_step": ms, "frames_per_s": batch / (ms * 1e-3), "loss": float(loss.detach())}
                 except Exception as exc:      # a variant that stock PyTorch cannot run (e.g. graph capture) is reported, not fatal
                     out["variants"][name] = {"error": repr(exc)[:160]}
                 torch.cuda.synchronize()

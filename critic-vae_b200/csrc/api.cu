@@ -21,6 +21,11 @@ static unsigned long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
 unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
+bool pdl_enabled() {
+    static const bool on = !(getenv("CVAE_PDL") && atoi(getenv("CVAE_PDL")) == 0);
+    return on;
+}
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;

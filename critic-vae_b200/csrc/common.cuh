@@ -69,6 +69,32 @@ int opt_in_smem(const void* func, size_t bytes);  // api.cu: raise a kernel's dy
         int rc__ = cvae::opt_in_smem(reinterpret_cast<const void*>(kern), (bytes));      \
         if (rc__ != CVAE_OK) return rc__;                                                \
     } while (0)
+// Programmatic dependent launch: every kernel of this library is launched with the stream-serialization attribute and
+// starts with grid_dependency_sync(), so its CTAs become resident (and run their prologue: barrier init, TMEM allocation,
+// tensor-map prefetch) while the previous kernel of the stream drains, and go on the moment that kernel's memory is
+// visible.  In a captured graph the edge becomes a programmatic one.  CVAE_PDL=0 launches without the attribute (the
+// device-side instructions are then no-ops).  RULE: nothing a predecessor writes may be read, and nothing it reads may
+// be written, before grid_dependency_sync().
+bool pdl_enabled();  // api.cu
+__device__ __forceinline__ void grid_dependency_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+
 int sm_count();     // cached multiprocessor count of the current device (api.cu)
 int* fault_flag();  // device address of the pipeline-fault flag (api.cu)
 

@@ -82,6 +82,32 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t tmem_t
     const bool valid = (vcol < a.W) && (r >= a.pad) && (n < a.B);
     const int h = r - a.pad, w = vcol;
     const size_t pix = ((size_t)n * a.H + h) * a.W + w;
+    if constexpr (EPI == CVAE_EPI_STATS && N == 32) {
+        // 32-channel layers (encoder conv 0): one thread owns one pixel's whole channel row, so the BatchNorm sums stay
+        // thread-private (s1 / s2 hold one entry per CHANNEL here) until flush_stats reduces them across the lanes once
+        // per kernel -- no shared-memory transpose per tile.  The sums are those of the bf16 values actually stored.
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tmem_tile + ((uint32_t)(warp * 32) << 16), r0);
+        tmem_ld16(tmem_tile + ((uint32_t)(warp * 32) << 16) + 16u, r1);
+        tmem_wait_ld();
+        if (valid) {
+            uint32_t p[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                p[i] = i < 8 ? pack_bf16x2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]))
+                             : pack_bf16x2(__uint_as_float(r1[2 * i - 16]), __uint_as_float(r1[2 * i - 15]));
+                const float lo = bf16_lo(p[i]), hi = bf16_hi(p[i]);
+                s1[2 * i] += lo;
+                s1[2 * i + 1] += hi;
+                s2[2 * i] = fmaf(lo, lo, s2[2 * i]);
+                s2[2 * i + 1] = fmaf(hi, hi, s2[2 * i + 1]);
+            }
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.c_total + nb * N);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+        }
+        return;
+    }
 #pragma unroll
     for (int g = 0; g < N / 16; ++g) {
         uint32_t raw[16];
@@ -176,7 +202,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t tmem_t
 
 template <int EPI, int N>
 __device__ __forceinline__ void flush_stats(const ConvArgs& a, int nb, int lane, float* s1, float* s2) {
-    if constexpr (EPI == CVAE_EPI_STATS) {
+    if constexpr (EPI == CVAE_EPI_STATS && N == 32) {      // thread-private per-channel sums (see epilogue_tile)
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float t1 = warp_sum(s1[c]), t2 = warp_sum(s2[c]);
+            if (lane == c) { m1 = t1; m2 = t2; }
+            s1[c] = s2[c] = 0.f;
+        }
+        atomicAdd(a.stats + nb * N + lane, (double)m1);
+        atomicAdd(a.stats + a.c_total + nb * N + lane, (double)m2);
+    } else if constexpr (EPI == CVAE_EPI_STATS) {
         if (lane < 16) {
 #pragma unroll
             for (int g = 0; g < N / 16; ++g) {
@@ -374,15 +410,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvAr
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    grid_dependency_sync();     // everything above touched only this CTA's shared memory and TMEM
     const uint32_t tmem_base = tmem_slot;
     const int n_items = a.num_chunks * a.n_blocks;
     const int spg = a.kpg / a.ksps;  // weight stages per channel group
 
     if (warp < 4) {
         // ================================ epilogue ================================================
-        float s1[(EPI == CVAE_EPI_STATS) ? N / 16 : 1], s2[(EPI == CVAE_EPI_STATS) ? N / 16 : 1];
+        constexpr int kStatRegs = (EPI != CVAE_EPI_STATS) ? 1 : (N == 32 ? 32 : N / 16);
+        float s1[kStatRegs], s2[kStatRegs];
 #pragma unroll
-        for (int g = 0; g < ((EPI == CVAE_EPI_STATS) ? N / 16 : 1); ++g) s1[g] = s2[g] = 0.f;
+        for (int g = 0; g < kStatRegs; ++g) s1[g] = s2[g] = 0.f;
         int cur_nb = -1;
         uint32_t it = 0;
         long long t_epi = 0;
@@ -532,7 +570,7 @@ static int launch_pipe(const ConvArgs& a, size_t smem, cudaStream_t stream) {
         fprintf(stderr, "conv_pipe<L%d,E%d,N%d> B=%d %dx%d planes=%dx%d ksteps=%d kpg=%d ksps=%d stages=%d%s tm=%d chunks=%d "
                         "nblk=%d smem=%zu grid=%d\n", LOADER, EPI, N, a.B, a.H, a.W, a.planes, a.ncg, a.ksteps, a.kpg, a.ksps,
                 a.nstages, a.resident ? "(resident)" : "", a.tm, a.num_chunks, a.n_blocks, smem, gx);
-    kern<<<gx, kPipeThreads, smem, stream>>>(a);
+    cvae::launch(kern, gx, kPipeThreads, smem, stream, a);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }

@@ -369,6 +369,7 @@ conv_wa_kernel(const WaArgs a, const __grid_constant__ CUtensorMap map0, const _
     tc_fence_before();
     if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
+    grid_dependency_sync();     // everything above touched only this CTA's shared memory and TMEM
     if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 16 + 9] = wa_now_ns();     // prologue done
     const uint32_t tmem_base = tmem_slot;
     const int items = a.nt * a.m_blocks;
@@ -613,11 +614,20 @@ static int launch_wa(const WaArgs& a, const CUtensorMap* maps, int grid, size_t 
     cfg.blockDim = dim3(kWaThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CL > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {      // programmatic dependent launch (common.cuh: launch / grid_dependency_sync)
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = CL > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     CVAE_CUDA(cudaLaunchKernelEx(&cfg, conv_wa_kernel<EPI, CL, J>, a, maps[0], maps[1], maps[2], maps[3], maps[4]));
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;

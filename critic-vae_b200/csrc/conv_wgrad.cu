@@ -28,6 +28,9 @@ static constexpr int kMaxGroups = 28;
 // experiment switches, read once at load time (never on the launch path)
 static const bool g_wg_debug = getenv("CVAE_DEBUG") != nullptr;
 static const bool g_wg_no_tma = getenv("CVAE_WG_NO_TMA") != nullptr;
+static const bool g_wg_no_stack = getenv("CVAE_WG_NO_STACK") != nullptr;
+static const int g_wg_stack_pw = getenv("CVAE_WG_STACK_PW") ? atoi(getenv("CVAE_WG_STACK_PW")) : 0;   // experiments: force the tap-stacked plan
+static const int g_wg_stack_ra = getenv("CVAE_WG_STACK_RA") ? atoi(getenv("CVAE_WG_STACK_RA")) : 0;
 static const int g_wg_kc = getenv("CVAE_WG_KC") ? atoi(getenv("CVAE_WG_KC")) : 0;
 static const int g_fold_linear = getenv("CVAE_FOLD_LINEAR") ? 1 : 0;
 // warps 0 .. kWgLoadWarps-1 load planes (the address arithmetic of a 16-byte-granular gather is latency bound with
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradAr
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    grid_dependency_sync();     // everything above touched only this CTA's shared memory and TMEM
     const uint32_t tmem_base = tmem_slot;
 
     const int my_chunks = (a.num_chunks - split + a.splits - 1) / a.splits;  // chunks split, split+S, ...
@@ -241,6 +245,7 @@ struct FoldArgs {
     int n;             // columns per normal group
     int bias_off;      // float offset of the ones pseudo-group ([m_total][16]) inside a split, -1: none
     int dbg_linear;
+    int stack;         // tap-stacked partial (launch_wgrad_stack): a group holds the taps of one (pair of) filter row(s), its n columns are (dx, ci)
     const float* partial;
     float* dw;         // [cout][cin][5][5]
     float* dbias;      // [cout]
@@ -304,6 +309,7 @@ __device__ __forceinline__ float fold_bias_term(const FoldArgs& f, const float* 
 // (10 MB per step in total).
 template <int kFoldLanes>
 __global__ void __launch_bounds__(256) wgrad_fold_kernel(const FoldArgs f) {
+    grid_dependency_sync();
     constexpr int kOut = 256 / kFoldLanes;   // outputs per block
     __shared__ float red[kFoldLanes][kOut + 1];
     const int total_w = 25 * f.cout * f.cin;
@@ -352,6 +358,7 @@ __global__ void __launch_bounds__(256) wgrad_fold_kernel(const FoldArgs f) {
 // Blocks past the weight range compute the bias gradient (scalar path).
 template <int kFoldLanes>
 __global__ void __launch_bounds__(256) wgrad_fold_rows_kernel(const FoldArgs f, int weight_blocks) {
+    grid_dependency_sync();
     constexpr int kOut = 256 / kFoldLanes;   // float4 outputs per block
     __shared__ float4 red[kFoldLanes][kOut];
     const int o = threadIdx.x % kOut, sl = threadIdx.x / kOut;
@@ -384,13 +391,19 @@ __global__ void __launch_bounds__(256) wgrad_fold_rows_kernel(const FoldArgs f, 
     size_t off[4];
     int nsrc = 1;
     if (f.kind == CVAE_WGRAD_5X5) {
-        off[0] = ((size_t)(ky * 5 + kx) * f.m_total + co) * f.n + ci;
+        if (f.stack) {   // group g = filter rows (2g, 2g+1) as (row block 1, row block 0) of 64 channels; group 2 = filter row 4 in block 0
+            const int g = ky < 4 ? (ky >> 1) : 2, j = ky < 4 ? 1 - (ky & 1) : 0;
+            off[0] = ((size_t)g * f.m_total + j * f.cout + co) * f.n + kx * f.cin + ci;
+        } else {
+            off[0] = ((size_t)(ky * 5 + kx) * f.m_total + co) * f.n + ci;
+        }
     } else {
         nsrc = 4;
 #pragma unroll
         for (int ab = 0; ab < 4; ++ab) {
-            const int t = phase_tap(ab >> 1, ky) * 3 + phase_tap(ab & 1, kx);
-            off[ab] = ((size_t)t * f.m_total + ab * f.cout + co) * f.n + ci;
+            const int ty = phase_tap(ab >> 1, ky), tx = phase_tap(ab & 1, kx);
+            off[ab] = f.stack ? ((size_t)ty * f.m_total + ab * f.cout + co) * f.n + tx * f.cin + ci
+                              : ((size_t)(ty * 3 + tx) * f.m_total + ab * f.cout + co) * f.n + ci;
         }
     }
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
@@ -424,7 +437,7 @@ template <int LA, int LB>
 static int launch_wgrad(const WgradArgs& a, size_t smem, dim3 grid, cudaStream_t stream) {
     auto kern = conv_wgrad_kernel<LA, LB>;
     CVAE_OPT_IN_SMEM(kern, smem);
-    kern<<<grid, kWgThreads, smem, stream>>>(a);
+    cvae::launch(kern, grid, kWgThreads, smem, stream, a);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -456,6 +469,13 @@ struct WgTmaArgs {
     int buf_bytes, a_region, nbuf;   // nbuf: 2..4 chunk buffers (TMA latency is longer than the MMAs of a short chunk)
     uint32_t tx_bytes;          // bytes of all boxes of one chunk
     int phase_maps;             // A column block q of M block mb: 1 -> tensor map mb*2+q (channel 0), 0 -> map 0, channel (mb*2+q)*64
+    // Tap-stacked variant for 32-channel operands (launch_wgrad_stack): 64-byte rows (SWIZZLE_64B) and accumulator groups whose
+    // N columns are several taps side by side -- column block i of B is the SAME tile one pixel (one row of the tile) further on.
+    int a_loads;                // A boxes per chunk: 2 (two 64-channel blocks), 4 (four 32-channel phase blocks) or 1 (block 1 = block 0 one virtual row on)
+    int a_row0;                 // rows mode: chunks start this many image rows early (1 when block 1 is the shifted block 0)
+    int a_kstep, b_kstep;       // descriptor units (16 B) per K = 16 step: 128 for 128-byte rows, 64 for 64-byte rows
+    int b_row_units;            // 16-byte units per B row (8 or 4)
+    uint32_t a_hi, b_hi;        // high descriptor words (SBO, version, swizzle type) of A and B
     int ones_off, ones_stride;  // bias pseudo-group operand: no-swizzle plane pair of ones after the buffers (0: none)
     int m_rows, groups_total, gpc, split_floats;
     int tap_row[kMaxGroups];    // dy * PW + dx per group
@@ -498,6 +518,7 @@ conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap map
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    grid_dependency_sync();     // everything above touched only this CTA's shared memory and TMEM
     const uint32_t tmem_base = tmem_slot;
     const int my_chunks = (a.num_chunks - split + a.splits - 1) / a.splits;
     const uint32_t smem_base = smem_u32(smem);
@@ -514,7 +535,7 @@ conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap map
                 int n, ha, hb;
                 if (a.rows_mode) {
                     n = chunk / a.blocks_per_image;
-                    ha = (chunk - n * a.blocks_per_image) * a.RA;
+                    ha = (chunk - n * a.blocks_per_image) * a.RA - a.a_row0;
                     hb = ha - a.pad;
                 } else {
                     n = chunk * a.NB;
@@ -522,9 +543,8 @@ conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap map
                 }
                 mbar_expect_tx(&bar_full[buf], a.tx_bytes);
                 const uint32_t A = smem_base + (uint32_t)buf * a.buf_bytes;
-                const uint32_t Bp = A + a.a_region + (uint32_t)a.b_box_row * 128u;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                const uint32_t Bp = A + a.a_region + (uint32_t)(a.b_box_row * a.b_row_units) * 16u;
+                for (int q = 0; q < a.a_loads; ++q) {
                     const int blk = mb * 2 + q;
                     tma_load_4d(A + (uint32_t)q * a.a_block_bytes, a.phase_maps ? mapsA[blk] : mapsA[0], a.phase_maps ? 0 : blk * 64, 0, ha, n,
                                 &bar_full[buf]);
@@ -540,12 +560,13 @@ conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap map
             bool alive = true;
             // swizzled MN-major descriptors: LBO = column-block stride, SBO = 1024 (8 rows), layout type 2; the K loop
             // moves both start addresses by 16 rows = 2048 B = 128 descriptor units
-            const uint32_t hi_sw = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t hi_sw = a.a_hi;
             const uint32_t a_lbo = (((uint32_t)a.a_block_bytes >> 4) & 0x3FFFu) << 16;
             const uint32_t b_lbo = (((uint32_t)a.b_block_bytes >> 4) & 0x3FFFu) << 16;
             const uint32_t hi_ones = (((uint32_t)a.ones_stride >> 4) & 0x3FFFu) | (1u << 14);   // no swizzle: SBO = plane stride
             const uint32_t ones_lbo = (128u >> 4) << 16;
             const int ksteps = a.kc >> 4;
+            const uint32_t a_step = (uint32_t)a.a_kstep;
             for (int i = 0; i < my_chunks && alive; ++i) {
                 const int buf = i % a.nbuf;
                 alive = mbar_wait(&bar_full[buf], (i / a.nbuf) & 1, a.fault);
@@ -563,25 +584,25 @@ conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap map
                         b_hi = hi_ones;
                         b_step = 16u;    // 16 pixel slots of 16 B
                     } else {
-                        b_lo = (B16 + (uint32_t)(a.b_base_row + a.tap_row[g]) * 8u) | b_lbo;
-                        b_hi = hi_sw;
-                        b_step = 128u;
+                        b_lo = (B16 + (uint32_t)((a.b_base_row + a.tap_row[g]) * a.b_row_units)) | b_lbo;
+                        b_hi = a.b_hi;
+                        b_step = (uint32_t)a.b_kstep;
                     }
                     uint32_t acc = i > 0 ? 1u : 0u;
                     int k = 0;
                     for (; k + 4 <= ksteps; k += 4) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            umma_bf16(col, ((uint64_t)hi_sw << 32) | (uint64_t)(a_lo + (uint32_t)(j * 128)),
+                            umma_bf16(col, ((uint64_t)hi_sw << 32) | (uint64_t)(a_lo + (uint32_t)j * a_step),
                                       ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)j * b_step), idesc, j == 0 ? acc : 1u);
                         acc = 1u;
-                        a_lo += 4u * 128u;
+                        a_lo += 4u * a_step;
                         b_lo += 4u * b_step;
                     }
                     for (; k < ksteps; ++k) {
                         umma_bf16(col, ((uint64_t)hi_sw << 32) | (uint64_t)a_lo, ((uint64_t)b_hi << 32) | (uint64_t)b_lo, idesc, acc);
                         acc = 1u;
-                        a_lo += 128u;
+                        a_lo += a_step;
                         b_lo += b_step;
                     }
                     col += (uint32_t)n;
@@ -730,6 +751,8 @@ static int launch_wgrad_tma(const cvae_wgrad_desc* d, const WgradArgs& base, int
     if (!enc_ok) return 1;
 
     t.m_rows = 128;
+    t.a_loads = 2; t.a_row0 = 0; t.a_kstep = 128; t.b_kstep = 128; t.b_row_units = 8;
+    t.a_hi = t.b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B (8 rows of 128 B), version 1, SWIZZLE_128B
     t.groups_total = base.groups_total; t.gpc = base.gpc; t.split_floats = base.split_floats;
     for (int g = 0; g < base.groups_total; ++g) {
         t.gn[g] = base.g[g].n;
@@ -744,7 +767,147 @@ static int launch_wgrad_tma(const cvae_wgrad_desc* d, const WgradArgs& base, int
                 d->kind, H, W, d->cout, d->cin, t.rows_mode ? "rows" : "images", t.NB, t.RA, t.kc, t.nbuf, t.num_chunks, splits, gsets, m_blocks,
                 t.buf_bytes, smem);
     dim3 grid(splits, gsets, m_blocks);
-    conv_wgrad_tma_kernel<<<grid, kWtThreads, smem, stream>>>(t, mA[0], mA[1], mA[2], mA[3], mB);
+    cvae::launch(conv_wgrad_tma_kernel, grid, kWtThreads, smem, stream, t, mA[0], mA[1], mA[2], mA[3], mB);
+    CVAE_LAUNCH_CHECK();
+    *splits_out = splits;
+    return CVAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tap-stacked variant of the TMA kernel for 32-channel inputs (encoder conv 1: 5x5, 32 -> 64; decoder conv 3 in phase
+// form: 3x3, 32 -> 4 x 32).  With N = 32 columns per tap the tensor pipe runs at a third of its rate and every tap is its
+// own MMA; here the B tile has 64-byte rows ([virtual pixel][32 ch], SWIZZLE_64B) and ONE accumulator group covers all
+// the dx of a filter row: column block i of the MN-major B descriptor is the same tile one pixel further on (LBO = 64 B),
+// so N = 5 x 32 = 160 (3 x 32 = 96).  With 64 output channels the M = 128 rows are stacked as well: row block 1 of A is
+// row block 0 one virtual image row further on (LBO = PW x 128 B), which makes it the filter row above -- 25 taps in
+// 3 MMAs per K step instead of 25.  Chunks are RA image rows; with the shifted A block they start one row early so that
+// both blocks see every image row exactly once, and RA x PW must then be a multiple of 16 (PW is widened with extra
+// zero columns -- out-of-bounds box columns -- until a good RA exists).
+// ---------------------------------------------------------------------------------------------------------------
+struct WgStackShape { int ndx, ngroups, n, mstack; long split_floats; };
+static bool wgrad_stack_shape(const cvae_wgrad_desc* d, WgStackShape& s) {
+    if (d->cin != 32) return false;
+    if (d->kind == CVAE_WGRAD_5X5 && d->cout == 64) { s.ndx = 5; s.mstack = 1; }
+    else if (d->kind == CVAE_WGRAD_PHASE && d->cout == 32) { s.ndx = 3; s.mstack = 0; }
+    else return false;
+    s.ngroups = 3;
+    s.n = s.ndx * 32;
+    s.split_floats = (long)s.ngroups * 128 * s.n + (d->dbias ? 128 * 16 : 0);
+    return true;
+}
+
+// returns 1 when the shape is not eligible (the caller goes on with the other variants)
+static int launch_wgrad_stack(const cvae_wgrad_desc* d, int H, int W, int pad, cudaStream_t stream, int max_splits, WgStackShape& s, int* splits_out,
+                              int* bias_off_out) {
+    if (g_wg_no_tma || g_wg_no_stack || !wgrad_stack_shape(d, s) || !tensor_map_encoder()) return 1;
+    const bool bias = d->dbias != nullptr;
+    WgTmaArgs t{};
+    t.pad = pad;
+    t.rows_mode = 1; t.NB = 1;
+    t.b_blocks = 1;
+    t.a_row0 = s.mstack;
+    t.a_loads = s.mstack ? 1 : 4;
+    const int a_row_bytes = s.mstack ? 128 : 64;
+    const size_t cap = 212 * 1024;
+    int splits = max_splits < 1 ? 1 : max_splits;
+    int best_pw = 0, best_ra = 0;
+    double best_cost = 1e30;
+    int PW = 0, halo = 0;
+    auto plan = [&](int pw, int RA) -> bool {
+        const int kreal = RA * pw;
+        if (s.mstack && (kreal & 15)) return false;
+        const int kc = (kreal + 15) / 16 * 16;
+        if (pw > 256 || RA + 2 * pad > 256) return false;
+        const int hl = pad * pw + pad;
+        const int a_rows = kc + (s.mstack ? pw : 0);
+        const int a_block = s.mstack ? pw * 128 : ((kc * 64 + 1023) & ~1023);       // LBO of A
+        const int a_region = s.mstack ? ((a_rows * 128 + 1023) & ~1023) : 4 * a_block;
+        const int b_box_row = 8;
+        const int b_rows = b_box_row + (RA + 2 * pad) * pw + (kc - kreal) + hl + 16;
+        const int b_bytes = (b_rows * 64 + 1023) & ~1023;
+        const size_t buf = (size_t)a_region + b_bytes;
+        const size_t ones = bias ? (size_t)2 * (((kc * 16) + 127) & ~127) : 0;
+        if (2 * buf + ones > cap || a_region >= (1 << 18) || b_bytes >= (1 << 18)) return false;
+        int nbuf = (int)((cap - ones) / buf);
+        t.nbuf = nbuf > 4 ? 4 : nbuf;
+        t.RA = RA; t.kc = kc;
+        t.b_box_row = b_box_row;
+        t.b_base_row = b_box_row + pad * pw;
+        t.a_block_bytes = a_block; t.b_block_bytes = 64;      // B: the next column block is the next pixel
+        t.a_region = a_region;
+        t.buf_bytes = (int)buf;
+        t.ones_off = bias ? (int)(t.nbuf * buf) : 0;
+        t.ones_stride = (kc * 16 + 127) & ~127;
+        t.tx_bytes = (uint32_t)((s.mstack ? (RA + 1) * pw * 128 : 4 * RA * pw * 64) + (RA + 2 * pad) * pw * 64);
+        t.blocks_per_image = (H + s.mstack + RA - 1) / RA;
+        t.num_chunks = d->batch * t.blocks_per_image;
+        PW = pw; halo = hl;
+        return true;
+    };
+    for (int pw = W + pad; pw <= W + pad + 8; ++pw)
+        for (int RA = 1; RA <= H + s.mstack; ++RA) {
+            if (!plan(pw, RA)) continue;
+            const int per_cta = (t.num_chunks + splits - 1) / splits;
+            double cost = (double)per_cta * (t.kc + 64);          // K per CTA plus a per-chunk overhead worth ~64 pixels
+            if (t.nbuf < 3) cost *= 1.15;
+            if (per_cta < 2) cost *= 2.0;
+            if (cost < best_cost) { best_cost = cost; best_pw = pw; best_ra = RA; }
+        }
+    if (g_wg_stack_pw > 0 && g_wg_stack_ra > 0 && plan(W + pad + g_wg_stack_pw - 1, g_wg_stack_ra)) { best_pw = W + pad + g_wg_stack_pw - 1; best_ra = g_wg_stack_ra; }
+    if (best_pw == 0 || !plan(best_pw, best_ra)) return 1;
+    if (splits > t.num_chunks) splits = t.num_chunks;
+    t.splits = splits;
+
+    CUtensorMap mA[4], mB;
+    bool ok = true;
+    if (s.mstack) {
+        ok = encode_map_4d(&mA[0], d->dy, d->cout, W, H, d->batch, d->cout, (long)W * d->cout, (long)H * W * d->cout, 64, PW, t.RA + 1, 1,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+        mA[1] = mA[2] = mA[3] = mA[0];
+        t.phase_maps = 0;
+        t.a_kstep = 128;
+        t.a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    } else {   // dY at [B][2H][2W][32]: one strided 32-channel view per output phase
+        const long c = d->cout;
+        for (int ab = 0; ab < 4 && ok; ++ab) {
+            const __nv_bfloat16* b0 = (const __nv_bfloat16*)d->dy + ((long)(ab >> 1) * 2 * W + (ab & 1)) * c;
+            ok = encode_map_4d(&mA[ab], b0, d->cout, W, H, d->batch, 2 * c, 2L * 2 * W * c, 4L * H * W * c, 32, PW, t.RA, 1, CU_TENSOR_MAP_SWIZZLE_64B);
+        }
+        t.phase_maps = 1;
+        t.a_kstep = 64;
+        t.a_hi = (512u >> 4) | (1u << 14) | (4u << 29);
+    }
+    ok = ok && encode_map_4d(&mB, d->x, d->cin, W, H, d->batch, d->cin, (long)W * d->cin, (long)H * W * d->cin, 32, PW, t.RA + 2 * pad, 1,
+                             CU_TENSOR_MAP_SWIZZLE_64B);
+    if (!ok) return 1;
+    t.b_kstep = 64; t.b_row_units = 4;
+    t.b_hi = (512u >> 4) | (1u << 14) | (4u << 29);           // SBO 512 B (8 rows of 64 B), version 1, SWIZZLE_64B
+
+    t.m_rows = 128;
+    t.groups_total = s.ngroups + (bias ? 1 : 0);
+    t.gpc = t.groups_total;
+    t.split_floats = (int)s.split_floats;
+    for (int g = 0; g < s.ngroups; ++g) {
+        const int dy = s.mstack ? (g == 0 ? -1 : g) : g - 1;      // block 0's filter row; block 1 (stacked M) is the row above
+        t.gn[g] = s.n;
+        t.gout[g] = g * 128 * s.n;
+        t.tap_row[g] = dy * PW - pad;
+    }
+    *bias_off_out = -1;
+    if (bias) {
+        t.gn[s.ngroups] = 16;
+        t.gout[s.ngroups] = s.ngroups * 128 * s.n;
+        t.tap_row[s.ngroups] = 0;
+        *bias_off_out = t.gout[s.ngroups];
+    }
+    t.partial = (float*)d->workspace; t.fault = fault_flag();
+    if (t.fault == nullptr) return 1;
+    const size_t smem = (size_t)t.nbuf * t.buf_bytes + (t.ones_off ? (size_t)2 * t.ones_stride : 0);
+    CVAE_OPT_IN_SMEM(conv_wgrad_tma_kernel, smem);
+    if (g_wg_debug)
+        fprintf(stderr, "conv_wgrad_stack kind %d %dx%d cout=%d cin=%d: PW=%d RA=%d kc=%d nbuf=%d chunks=%d splits=%d n=%d buf=%d smem=%zu\n", d->kind, H, W,
+                d->cout, d->cin, PW, t.RA, t.kc, t.nbuf, t.num_chunks, splits, s.n, t.buf_bytes, smem);
+    cvae::launch(conv_wgrad_tma_kernel, dim3(splits, 1, 1), kWtThreads, smem, stream, t, mA[0], mA[1], mA[2], mA[3], mB);
     CVAE_LAUNCH_CHECK();
     *splits_out = splits;
     return CVAE_OK;
@@ -804,10 +967,29 @@ static bool wgrad_shape(const cvae_wgrad_desc* d, WgShape& s) {
     return true;
 }
 
-extern "C" int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d) {
+// splits x floats-per-split of the variant the launcher would pick for exactly this descriptor
+static int64_t wgrad_workspace_exact(const cvae_wgrad_desc* d) {
     WgShape s;
-    if (!d || !wgrad_shape(d, s)) return -1;
-    return (int64_t)s.max_splits * s.split_floats * 4;   // both kernel variants use <= max_splits splits
+    if (!wgrad_shape(d, s)) return -1;
+    int64_t bytes = (int64_t)s.max_splits * s.split_floats * 4;   // the plane and the TMA variant use <= max_splits splits
+    WgStackShape st;
+    if (wgrad_stack_shape(d, st)) {                               // the tap-stacked variant: one CTA per SM, wider partials
+        const int64_t sb = (int64_t)(d->splits > 0 ? d->splits : sm_count()) * st.split_floats * 4;
+        if (sb > bytes) bytes = sb;
+    }
+    return bytes;
+}
+
+extern "C" int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d) {
+    if (!d) return -1;
+    // The bias pseudo-group changes both the partial size and the split count: callers routinely size the workspace before
+    // they fill in dbias, so the answer covers both forms of the call.
+    cvae_wgrad_desc with = *d, without = *d;
+    with.dbias = (void*)(uintptr_t)8;
+    without.dbias = nullptr;
+    const int64_t a = wgrad_workspace_exact(&with), b = wgrad_workspace_exact(&without);
+    if (a < 0 || b < 0) return -1;
+    return a > b ? a : b;
 }
 
 extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
@@ -815,6 +997,11 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
     CVAE_REQUIRE(d != nullptr, CVAE_EINVAL, "conv_wgrad: null descriptor");
     CVAE_REQUIRE(d->x && d->dy && d->dw && d->workspace, CVAE_EINVAL, "conv_wgrad: null tensor");
     CVAE_REQUIRE(d->batch > 0, CVAE_EINVAL, "conv_wgrad: empty batch");
+    if (d->workspace_bytes > 0) {
+        const int64_t need = wgrad_workspace_exact(d);
+        CVAE_REQUIRE(need >= 0 && need <= d->workspace_bytes, CVAE_EINVAL, "conv_wgrad: workspace of %lld bytes, this call needs %lld",
+                     (long long)d->workspace_bytes, (long long)need);
+    }
 
     WgradArgs a{};
     FoldArgs f{};
@@ -964,10 +1151,22 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
         fprintf(stderr, "conv_wgrad kind %d B=%d %dx%d cout=%d cin=%d: n=%d groups=%d gpc=%d gsets=%d mblocks=%d splits=%d kc=%d chunks=%d "
                         "buf=%d B smem=%zu\n", d->kind, d->batch, H, W, d->cout, d->cin, n, a.groups_total, a.gpc, gsets, a.m_blocks, splits,
                 a.kc, a.num_chunks, a.buf_bytes, (size_t)2 * a.buf_bytes);
-    int tma_splits = shape.max_splits;
-    int rc = launch_wgrad_tma(d, a, n, gsets, H, W, pad, stream, &tma_splits);
+    WgStackShape stack{};
+    int stack_splits = 0, stack_bias_off = -1;
+    int rc = launch_wgrad_stack(d, H, W, pad, stream, d->splits > 0 ? d->splits : sm_count(), stack, &stack_splits, &stack_bias_off);
     if (rc < 0) return rc;
-    if (rc == CVAE_OK) splits = tma_splits;   // TMA variant launched with its own chunking
+    const bool stacked = rc == CVAE_OK;
+    int tma_splits = shape.max_splits;
+    if (!stacked) rc = launch_wgrad_tma(d, a, n, gsets, H, W, pad, stream, &tma_splits);
+    if (rc < 0) return rc;
+    if (stacked) {                                // tap-stacked TMA variant: its own partial layout (FoldArgs::stack)
+        splits = stack_splits;
+        n = stack.n;
+        a.split_floats = (int)stack.split_floats;
+        a.m_total = 128;
+        f.bias_off = stack_bias_off;
+        f.stack = 1;
+    } else if (rc == CVAE_OK) splits = tma_splits;   // TMA variant launched with its own chunking
     else if (la == CVAE_LOAD_NHWC) rc = launch_wgrad<CVAE_LOAD_NHWC, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     else if (la == CVAE_LOAD_S2D) rc = launch_wgrad<CVAE_LOAD_S2D, CVAE_LOAD_NHWC>(a, smem, grid, stream);
     else if (la == CVAE_LOAD_NCHW3) rc = launch_wgrad<CVAE_LOAD_NCHW3, CVAE_LOAD_NHWC>(a, smem, grid, stream);
@@ -994,14 +1193,14 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
     {                                                                                                 \
         const int wb = (total4 + 256 / (L_) - 1) / (256 / (L_));                                      \
         const int bb = f.dbias ? (d->cout + 256 / (L_) - 1) / (256 / (L_)) : 0;                       \
-        wgrad_fold_rows_kernel<L_><<<wb + bb, 256, 0, stream>>>(f, wb);                               \
+        cvae::launch(wgrad_fold_rows_kernel<L_>, wb + bb, 256, 0, stream, f, wb);                               \
     }
             if (splits >= 48) CVAE_FOLD_ROWS(8)
             else if (splits >= 16) CVAE_FOLD_ROWS(4)
             else CVAE_FOLD_ROWS(2)
 #undef CVAE_FOLD_ROWS
         } else {
-            wgrad_fold_kernel<8><<<(total + 31) / 32, 256, 0, stream>>>(f);
+            cvae::launch(wgrad_fold_kernel<8>, (total + 31) / 32, 256, 0, stream, f);
         }
     }
     CVAE_LAUNCH_CHECK();

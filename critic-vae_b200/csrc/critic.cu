@@ -62,6 +62,7 @@ __device__ __forceinline__ void conv_relu_pool(const float* __restrict__ in, con
 
 __global__ void __launch_bounds__(256, 1)
 critic_fwd_kernel(int frames, const float* __restrict__ x, const float* __restrict__ weights, float* __restrict__ pred) {
+    grid_dependency_sync();
     extern __shared__ float sm[];
     float* wsm = sm;                          // 11873 (+3 pad)
     float* in = wsm + 11876;                  // 3 x 64 x 64
@@ -119,7 +120,7 @@ extern "C" int cvae_critic_fwd(int frames, const float* x, const float* weights,
     const size_t smem = sizeof(float) * (11876 + 3 * 4096 + 8 * 1024 + 8 * 256 + 8 * 64 + 256 + 64);
     CVAE_OPT_IN_SMEM(critic_fwd_kernel, smem);
     const int grid = frames < sm_count() ? frames : sm_count();
-    critic_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(frames, x, weights, pred);
+    cvae::launch(critic_fwd_kernel, grid, 256, smem, (cudaStream_t)stream, frames, x, weights, pred);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }

@@ -25,6 +25,7 @@ __global__ void bn_finalize_kernel(int C, double count, int training, const doub
                                    const float* gamma, const float* beta, const float* conv_bias,
                                    float* rmean, float* rvar, long long* nbt, float momentum, float eps,
                                    float* ss) {
+    grid_dependency_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float mean, invstd;
@@ -53,6 +54,92 @@ __global__ void bn_finalize_kernel(int C, double count, int training, const doub
 
 __device__ __forceinline__ float act_fn(int act, float x) { return act == 0 ? fmaxf(x, 0.f) : tanhf(x); }
 
+// bn_finalize + bn_pool_act_fwd in ONE launch (the finalize kernel is a single small block: its 3 us plus a launch
+// boundary, four times per forward pass, sat on the main chain).  Every CTA recomputes scale / shift / mean / invstd of
+// all C <= 256 channels from the conv epilogue's statistics into shared memory (identical arithmetic in every CTA);
+// block 0 also publishes them for the backward pass and updates the running buffers.
+struct BnFusedArgs {
+    double count;
+    int training;
+    const double* stats;
+    const float *gamma, *beta, *conv_bias;
+    float *rmean, *rvar;
+    long long* nbt;
+    float momentum, eps;
+    float* ss_out;
+};
+__global__ void __launch_bounds__(256) bn_fused_fwd_kernel(int B, int H, int W, int C, int act, const uint4* __restrict__ x, const BnFusedArgs f,
+                                                           uint4* __restrict__ y, uint4* __restrict__ xhat_max, uint16_t* __restrict__ argmax) {
+    grid_dependency_sync();
+    __shared__ __align__(16) float ss[4 * 256];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float mean, invstd;
+        if (f.training) {
+            const double m = f.stats[c] / f.count;
+            double var = f.stats[C + c] / f.count - m * m;
+            if (var < 0) var = 0;
+            mean = (float)m;
+            invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+            if (blockIdx.x == 0) {
+                const double unbiased = f.count > 1 ? var * f.count / (f.count - 1) : var;
+                f.rmean[c] = (1.f - f.momentum) * f.rmean[c] + f.momentum * (float)(m + (double)f.conv_bias[c]);
+                f.rvar[c] = (1.f - f.momentum) * f.rvar[c] + f.momentum * (float)unbiased;
+                if (c == 0 && f.nbt) f.nbt[0] += 1;
+            }
+        } else {
+            mean = f.rmean[c] - f.conv_bias[c];
+            invstd = 1.f / sqrtf(f.rvar[c] + f.eps);
+        }
+        const float sc = f.gamma[c] * invstd;
+        ss[c] = sc;
+        ss[C + c] = f.beta[c] - mean * sc;
+        ss[2 * C + c] = mean;
+        ss[3 * C + c] = invstd;
+        if (blockIdx.x == 0) {
+            f.ss_out[c] = sc; f.ss_out[C + c] = ss[C + c]; f.ss_out[2 * C + c] = mean; f.ss_out[3 * C + c] = invstd;
+        }
+    }
+    __syncthreads();
+    const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const long long total = (long long)B * Ho * Wo * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cg);
+        long long p = i / cg;
+        const int wo = (int)(p % Wo); p /= Wo;
+        const int ho = (int)(p % Ho);
+        const int n = (int)(p / Ho);
+        const float* sc = ss + c8 * 8;
+        const float* sh = ss + C + c8 * 8;
+        const size_t base = ((size_t)(n * H + 2 * ho) * W + 2 * wo) * cg + c8;
+        F8 m, xm;
+        uint32_t am = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const F8 v = unpack8(__ldg(x + base + (size_t)(q >> 1) * W * cg + (size_t)(q & 1) * cg));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float b = fmaf(v.v[e], sc[e], sh[e]);
+                if (q == 0 || b > m.v[e]) {   // first maximum wins, like nn.MaxPool2d
+                    m.v[e] = b;
+                    xm.v[e] = v.v[e];
+                    am = (am & ~(3u << (2 * e))) | ((uint32_t)q << (2 * e));
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m.v[e] = act_fn(act, m.v[e]);
+        y[i] = pack8(m);
+        if (xhat_max != nullptr) {
+            const float* mean = ss + 2 * C + c8 * 8;
+            const float* inv = ss + 3 * C + c8 * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xm.v[e] = (xm.v[e] - mean[e]) * inv[e];
+            xhat_max[i] = pack8(xm);
+            argmax[i] = (uint16_t)am;
+        }
+    }
+}
+
 // y = act(maxpool2x2(x*scale + shift)); x bf16 NHWC [B][H][W][C] -> y bf16 NHWC [B][H/2][W/2][C].
 // Training also saves what the backward needs per pooled element, so it does not have to redo the
 // normalisation of all four positions: the normalised value at the arg-max position (bf16) and the
@@ -60,6 +147,7 @@ __device__ __forceinline__ float act_fn(int act, float x) { return act == 0 ? fm
 __global__ void bn_pool_act_fwd_kernel(int B, int H, int W, int C, int act, const uint4* __restrict__ x,
                                        const float* __restrict__ ss, uint4* __restrict__ y,
                                        uint4* __restrict__ xhat_max, uint16_t* __restrict__ argmax) {
+    grid_dependency_sync();
     const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
     const long long total = (long long)B * Ho * Wo * cg;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -115,6 +203,7 @@ __global__ void bn_pool_act_bwd_kernel(int B, int H, int W, int C, int act, cons
                                        const uint4* __restrict__ xhat_max, const uint16_t* __restrict__ argmax,
                                        const float* __restrict__ ss, const float* __restrict__ gamma,
                                        double* sums, uint4* __restrict__ dx, float* dgamma, float* dbeta) {
+    grid_dependency_sync();
     extern __shared__ float red[];  // PASS 0: [blockDim][16]
     const int cg = C >> 3, Ho = H >> 1, Wo = W >> 1;
     const int c8 = threadIdx.x % cg;
@@ -205,6 +294,7 @@ static constexpr int kLatRows = 64;
 __global__ void __launch_bounds__(256) latent_fwd_kernel(int B, int sample, const float* __restrict__ ml, const float* __restrict__ eps,
                                                          const float* __restrict__ pred, float* __restrict__ zc,
                                                          double* __restrict__ kld_partial) {
+    grid_dependency_sync();
     __shared__ __align__(16) float stage[kLatRows * 33];
     __shared__ double red[8];
     const int tid = threadIdx.x;
@@ -259,6 +349,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(int B, int sample, cons
 __global__ void latent_bwd_kernel(int B, const float* __restrict__ ml, const float* __restrict__ eps,
                                   const float* __restrict__ dzc, const float* __restrict__ dmu_ext,
                                   const float* __restrict__ dlv_ext, float kld_grad_scale, float* __restrict__ dml) {
+    grid_dependency_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * 8) return;
     const long long b = i >> 3;
@@ -296,6 +387,7 @@ __global__ void latent_bwd_kernel(int B, const float* __restrict__ ml, const flo
 __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, const long long* __restrict__ step, float lr, float b1, float b2,
                             float eps, float grad_scale) {
+    grid_dependency_sync();
     const double t = (double)(step[0] + 1);
     const float bc1 = (float)(1.0 - pow((double)b1, t));
     const float sq_bc2 = (float)sqrt(1.0 - pow((double)b2, t));
@@ -310,11 +402,13 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
         p[i] = p[i] - step_size * (mi / denom);
     }
 }
-__global__ void adam_tick_kernel(long long* step) { step[0] += 1; }
+__global__ void adam_tick_kernel(long long* step) {
+    grid_dependency_sync(); step[0] += 1; }
 
 // uint8 HWC frames -> fp32 NCHW in [0,1]: astype(float32) / 255 then HWC->CHW, exactly
 // vae_utility.py:324-328,337-341 (adjust_values + transpose), so the bits match the reference's input.
 __global__ void frames_u8_kernel(long long n_pix, const uint8_t* __restrict__ src, float* __restrict__ dst) {
+    grid_dependency_sync();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (long long)gridDim.x * blockDim.x) {
         const long long f = i >> 12;
         const int p = (int)(i & 4095);
@@ -345,7 +439,7 @@ extern "C" int cvae_bn_finalize(int channels, int64_t count, int training, const
     CVAE_REQUIRE(channels > 0 && count > 0, CVAE_EINVAL, "bn_finalize: empty");
     CVAE_REQUIRE(gamma && beta && conv_bias && running_mean && running_var && scale_shift, CVAE_EINVAL, "bn_finalize: null tensor");
     CVAE_REQUIRE(!training || stats, CVAE_EINVAL, "bn_finalize: training needs stats");
-    bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    cvae::launch(bn_finalize_kernel, (channels + 127) / 128, 128, 0, (cudaStream_t)stream, 
         channels, (double)count, training, stats, gamma, beta, conv_bias, running_mean, running_var,
         (long long*)num_batches_tracked, momentum, eps, scale_shift);
     CVAE_LAUNCH_CHECK();
@@ -359,9 +453,26 @@ extern "C" int cvae_bn_pool_act_fwd(int batch, int height, int width, int channe
     CVAE_REQUIRE(conv_out && scale_shift && out, CVAE_EINVAL, "bn_pool_act_fwd: null tensor");
     CVAE_REQUIRE((xhat_max == nullptr) == (argmax == nullptr), CVAE_EINVAL, "bn_pool_act_fwd: xhat_max and argmax go together");
     const long long items = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
-    bn_pool_act_fwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+    cvae::launch(bn_pool_act_fwd_kernel, grid_for(items, 256), 256, 0, (cudaStream_t)stream, 
         batch, height, width, channels, act, (const uint4*)conv_out, scale_shift, (uint4*)out, (uint4*)xhat_max,
         (uint16_t*)argmax);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_bn_fwd(int batch, int height, int width, int channels, int act, int training, const void* conv_out,
+                           const double* stats, const float* gamma, const float* beta, const float* conv_bias, float* running_mean,
+                           float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* scale_shift, void* out,
+                           void* xhat_max, void* argmax, void* stream) {
+    CVAE_REQUIRE(batch > 0 && height % 2 == 0 && width % 2 == 0 && channels % 8 == 0 && channels <= 256, CVAE_EINVAL, "bn_fwd: shape");
+    CVAE_REQUIRE(conv_out && gamma && beta && conv_bias && running_mean && running_var && scale_shift && out, CVAE_EINVAL, "bn_fwd: null tensor");
+    CVAE_REQUIRE(!training || stats, CVAE_EINVAL, "bn_fwd: training needs stats");
+    CVAE_REQUIRE((xhat_max == nullptr) == (argmax == nullptr), CVAE_EINVAL, "bn_fwd: xhat_max and argmax go together");
+    const long long items = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
+    BnFusedArgs f{(double)batch * height * width, training, stats, gamma, beta, conv_bias, running_mean, running_var,
+                  (long long*)num_batches_tracked, momentum, eps, scale_shift};
+    cvae::launch(bn_fused_fwd_kernel, grid_for(items, 256), 256, 0, (cudaStream_t)stream, batch, height, width, channels, act, (const uint4*)conv_out, f,
+                                                                               (uint4*)out, (uint4*)xhat_max, (uint16_t*)argmax);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -382,11 +493,11 @@ extern "C" int cvae_bn_pool_act_bwd(int batch, int height, int width, int channe
     long long blocks = (npix + lanes - 1) / lanes;
     const long long cap = (long long)sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    bn_pool_act_bwd_kernel<0><<<(int)blocks, threads, threads * 16 * sizeof(float), stream>>>(
+    cvae::launch(bn_pool_act_bwd_kernel<0>, (int)blocks, threads, threads * 16 * sizeof(float), stream, 
         batch, height, width, channels, act, (const uint4*)conv_out, (const uint4*)act_out, (const uint4*)d_act,
         (const uint4*)xhat_max, (const uint16_t*)argmax, scale_shift, gamma, sums, nullptr, nullptr, nullptr);
     CVAE_LAUNCH_CHECK();
-    bn_pool_act_bwd_kernel<1><<<(int)blocks, threads, 0, stream>>>(
+    cvae::launch(bn_pool_act_bwd_kernel<1>, (int)blocks, threads, 0, stream, 
         batch, height, width, channels, act, (const uint4*)conv_out, (const uint4*)act_out, (const uint4*)d_act,
         (const uint4*)xhat_max, (const uint16_t*)argmax, scale_shift, gamma, sums, (uint4*)d_conv, dgamma, dbeta);
     CVAE_LAUNCH_CHECK();
@@ -399,7 +510,7 @@ extern "C" int cvae_latent_fwd(int batch, int sample, const float* mu_logvar, co
                                const float* pred, float* z_pred, double* kld_partial, void* stream) {
     CVAE_REQUIRE(batch > 0 && mu_logvar && pred && z_pred && (!sample || eps), CVAE_EINVAL, "latent_fwd: bad argument");
     CVAE_REQUIRE(((uintptr_t)mu_logvar | (uintptr_t)eps | (uintptr_t)z_pred) % 16 == 0, CVAE_EINVAL, "latent_fwd: tensors must be 16-byte aligned");
-    latent_fwd_kernel<<<cvae_latent_kld_partials(batch), 256, 0, (cudaStream_t)stream>>>(batch, sample, mu_logvar, eps, pred, z_pred, kld_partial);
+    cvae::launch(latent_fwd_kernel, cvae_latent_kld_partials(batch), 256, 0, (cudaStream_t)stream, batch, sample, mu_logvar, eps, pred, z_pred, kld_partial);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -410,7 +521,7 @@ extern "C" int cvae_latent_bwd(int batch, const float* mu_logvar, const float* e
     CVAE_REQUIRE(((uintptr_t)mu_logvar | (uintptr_t)eps | (uintptr_t)dmu_ext | (uintptr_t)dlogvar_ext | (uintptr_t)d_mu_logvar) % 16 == 0, CVAE_EINVAL,
                  "latent_bwd: tensors must be 16-byte aligned");
     const long long items = (long long)batch * 8;
-    latent_bwd_kernel<<<(int)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(batch, mu_logvar, eps, d_z_pred, dmu_ext, dlogvar_ext,
+    cvae::launch(latent_bwd_kernel, (int)((items + 255) / 256), 256, 0, (cudaStream_t)stream, batch, mu_logvar, eps, d_z_pred, dmu_ext, dlogvar_ext,
                                                                                    kld_grad_scale, d_mu_logvar);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
@@ -420,7 +531,7 @@ extern "C" int cvae_frames_u8_to_f32(int frames, const uint8_t* hwc_u8, float* n
     CVAE_REQUIRE(frames >= 0 && (frames == 0 || (hwc_u8 && nchw_f32)), CVAE_EINVAL, "frames_u8_to_f32: bad argument");
     if (frames == 0) return CVAE_OK;
     const long long n = (long long)frames * 4096;
-    frames_u8_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, hwc_u8, nchw_f32);
+    cvae::launch(frames_u8_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, n, hwc_u8, nchw_f32);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -429,10 +540,10 @@ extern "C" int cvae_adam_step(int64_t n, float* params, const float* grads, floa
                               int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale,
                               void* stream) {
     CVAE_REQUIRE(n > 0 && params && grads && exp_avg && exp_avg_sq && step, CVAE_EINVAL, "adam_step: bad argument");
-    adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq,
+    cvae::launch(adam_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq,
                                                                     (const long long*)step, lr, beta1, beta2, eps, grad_scale);
     CVAE_LAUNCH_CHECK();
-    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)step);
+    cvae::launch(adam_tick_kernel, 1, 1, 0, (cudaStream_t)stream, (long long*)step);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }

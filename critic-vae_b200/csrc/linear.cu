@@ -25,6 +25,7 @@ static constexpr size_t kFcSmem = (size_t)kFcSlice * 64 * 4 + (size_t)kFcRows * 
 __global__ void __cluster_dims__(kFcSplit, 1, 1) __launch_bounds__(256)
 fc_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restrict__ wfc,
               const float* __restrict__ bmu, const float* __restrict__ bvar, float* __restrict__ ml, int* fault) {
+    grid_dependency_sync();
     extern __shared__ __align__(128) uint8_t fc_smem[];
     float* sw = reinterpret_cast<float*>(fc_smem);                                        // [512][64]
     uint32_t* sa = reinterpret_cast<uint32_t*>(fc_smem + (size_t)kFcSlice * 64 * 4);      // [16][256] bf16 pairs
@@ -81,6 +82,7 @@ fc_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restric
 // ---- fc backward (data): da[b][k'] = sum_j dml[b][j] * wfc[k'][j]  (gradient w.r.t. the Tanh output) ----
 __global__ void fc_bwd_data_kernel(int B, const float* __restrict__ dml, const float* __restrict__ wfc,
                                    __nv_bfloat16* __restrict__ da) {
+    grid_dependency_sync();
     __shared__ float sd[8][64];
     const int b0 = blockIdx.x * 8;
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
@@ -115,6 +117,7 @@ static constexpr int kWLanes = 8;
 __global__ void __launch_bounds__(256) fc_bwd_weight_kernel(int B, const float* __restrict__ dml, const __nv_bfloat16* __restrict__ a,
                                                             float* __restrict__ dwmu, float* __restrict__ dwvar,
                                                             float* __restrict__ dbmu, float* __restrict__ dbvar) {
+    grid_dependency_sync();
     __shared__ float red[32][65];
     const int kq = threadIdx.x & 31, bl = threadIdx.x >> 5;
     const int kp = blockIdx.x * 32 + kq;  // k' in NHWC order
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(256) fc_bwd_weight_kernel(int B, const float* 
 // ---- decoder_input forward: h[b][k'] = sum_i zc[b][i] * wdec[i][k'] + wdec[33][k'] -> bf16 NHWC ------
 __global__ void decin_fwd_kernel(int B, const float* __restrict__ zc, const float* __restrict__ wdec,
                                  __nv_bfloat16* __restrict__ h) {
+    grid_dependency_sync();
     __shared__ float sz[8][33];
     const int b0 = blockIdx.y * 8;
     for (int i = threadIdx.x; i < 8 * 33; i += blockDim.x) {
@@ -190,6 +194,7 @@ static constexpr int kDdRows = 16, kDdSplit = 8, kDdSlice = 4096 / kDdSplit, kDd
 static constexpr size_t kDdSmem = (size_t)33 * kDdWStride * 4 + (size_t)kDdRows * kDdSlice * 2;
 __global__ void __cluster_dims__(kDdSplit, 1, 1) __launch_bounds__(256)
 decin_bwd_data_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* __restrict__ wdec, float* __restrict__ dzc, int* fault) {
+    grid_dependency_sync();
     extern __shared__ __align__(128) uint8_t dd_smem[];
     float* sw = reinterpret_cast<float*>(dd_smem);                                            // [33][516]
     uint32_t* sd = reinterpret_cast<uint32_t*>(dd_smem + (size_t)33 * kDdWStride * 4);         // [16][256] bf16 pairs
@@ -249,6 +254,7 @@ decin_bwd_data_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* 
 // same decomposition as fc_bwd_weight_kernel: 32 k' x 8 batch lanes, fixed-order combine.
 __global__ void __launch_bounds__(256) decin_bwd_weight_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* __restrict__ zc,
                                                                float* __restrict__ dw, float* __restrict__ db) {
+    grid_dependency_sync();
     __shared__ float red[32][35];
     const int kq = threadIdx.x & 31, bl = threadIdx.x >> 5;
     const int kp = blockIdx.x * 32 + kq;
@@ -289,7 +295,7 @@ extern "C" int cvae_fc_fwd(int batch, const void* act, const float* wfc, const f
     CVAE_OPT_IN_SMEM(fc_fwd_kernel, kFcSmem);
     int* fault = fault_flag();
     CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "fc_fwd: fault flag unavailable");
-    fc_fwd_kernel<<<((batch + kFcRows - 1) / kFcRows) * kFcSplit, 256, kFcSmem, stream>>>(batch, (const __nv_bfloat16*)act, wfc, bias_mu,
+    cvae::launch(fc_fwd_kernel, ((batch + kFcRows - 1) / kFcRows) * kFcSplit, 256, kFcSmem, stream, batch, (const __nv_bfloat16*)act, wfc, bias_mu,
                                                                                           bias_var, mu_logvar, fault);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
@@ -302,12 +308,12 @@ extern "C" int cvae_fc_bwd(int batch, const float* d_mu_logvar, const void* act,
     CVAE_REQUIRE(batch > 0 && d_mu_logvar && (d_act || want_w), CVAE_EINVAL, "fc_bwd: bad argument");
     if (d_act) {
         CVAE_REQUIRE(wfc != nullptr, CVAE_EINVAL, "fc_bwd: data gradient needs the packed weights");
-        fc_bwd_data_kernel<<<dim3((batch + 7) / 8, 4), 256, 0, stream>>>(batch, d_mu_logvar, wfc, (__nv_bfloat16*)d_act);
+        cvae::launch(fc_bwd_data_kernel, dim3((batch + 7) / 8, 4), 256, 0, stream, batch, d_mu_logvar, wfc, (__nv_bfloat16*)d_act);
         CVAE_LAUNCH_CHECK();
     }
     if (want_w) {
         CVAE_REQUIRE(act && dw_mu && dw_var && db_mu && db_var, CVAE_EINVAL, "fc_bwd: weight gradient outputs go together");
-        fc_bwd_weight_kernel<<<4096 / 32, 256, 0, stream>>>(batch, d_mu_logvar, (const __nv_bfloat16*)act, dw_mu, dw_var, db_mu, db_var);
+        cvae::launch(fc_bwd_weight_kernel, 4096 / 32, 256, 0, stream, batch, d_mu_logvar, (const __nv_bfloat16*)act, dw_mu, dw_var, db_mu, db_var);
         CVAE_LAUNCH_CHECK();
     }
     return CVAE_OK;
@@ -315,7 +321,7 @@ extern "C" int cvae_fc_bwd(int batch, const float* d_mu_logvar, const void* act,
 
 extern "C" int cvae_decin_fwd(int batch, const float* z_pred, const float* wdec, void* out, void* stream) {
     CVAE_REQUIRE(batch > 0 && z_pred && wdec && out, CVAE_EINVAL, "decin_fwd: bad argument");
-    decin_fwd_kernel<<<dim3(4096 / 128, (batch + 7) / 8), 128, 0, (cudaStream_t)stream>>>(batch, z_pred, wdec, (__nv_bfloat16*)out);
+    cvae::launch(decin_fwd_kernel, dim3(4096 / 128, (batch + 7) / 8), 128, 0, (cudaStream_t)stream, batch, z_pred, wdec, (__nv_bfloat16*)out);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -329,13 +335,13 @@ extern "C" int cvae_decin_bwd(int batch, const void* d_out, const float* z_pred,
         CVAE_OPT_IN_SMEM(decin_bwd_data_kernel, kDdSmem);
         int* fault = fault_flag();
         CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "decin_bwd: fault flag unavailable");
-        decin_bwd_data_kernel<<<((batch + kDdRows - 1) / kDdRows) * kDdSplit, 256, kDdSmem, stream>>>(
+        cvae::launch(decin_bwd_data_kernel, ((batch + kDdRows - 1) / kDdRows) * kDdSplit, 256, kDdSmem, stream, 
             batch, (const __nv_bfloat16*)d_out, wdec, d_z_pred, fault);
         CVAE_LAUNCH_CHECK();
     }
     if (dw || db) {
         CVAE_REQUIRE(z_pred && dw && db, CVAE_EINVAL, "decin_bwd: weight gradient outputs go together");
-        decin_bwd_weight_kernel<<<4096 / 32, 256, 0, stream>>>(batch, (const __nv_bfloat16*)d_out, z_pred, dw, db);
+        cvae::launch(decin_bwd_weight_kernel, 4096 / 32, 256, 0, stream, batch, (const __nv_bfloat16*)d_out, z_pred, dw, db);
         CVAE_LAUNCH_CHECK();
     }
     return CVAE_OK;

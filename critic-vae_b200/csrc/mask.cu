@@ -12,6 +12,7 @@ namespace cvae {
 
 __global__ void diff_grey_kernel(int frames, const float* __restrict__ hi, const float* __restrict__ lo,
                                  double* __restrict__ diff, double* __restrict__ maxv) {
+    grid_dependency_sync();
     __shared__ double red[8];
     const int f = blockIdx.x;
     const float* h = hi + (size_t)f * 3 * 4096;
@@ -39,6 +40,7 @@ __global__ void diff_grey_kernel(int frames, const float* __restrict__ hi, const
 __global__ void mask_iou_kernel(int frames, const double* __restrict__ diff, const uint8_t* __restrict__ gt,
                                 double mean_max, double factor, int thr, uint8_t* __restrict__ diff_u8,
                                 uint8_t* __restrict__ mask, unsigned long long* __restrict__ hist) {
+    grid_dependency_sync();
     __shared__ unsigned int sh[512];            // [gt][value]
     __shared__ __align__(16) uint8_t q[4096];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) sh[i] = 0;
@@ -95,6 +97,7 @@ __global__ void mask_iou_kernel(int frames, const double* __restrict__ diff, con
 // counts[t] = (tp, fn, fp) for threshold thr[t]: T = value > thr (vae_utility.py:157,57-59)
 __global__ void iou_counts_kernel(const unsigned long long* __restrict__ hist, int nthr, const int* __restrict__ thr,
                                   long long* __restrict__ counts) {
+    grid_dependency_sync();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthr) return;
     long long tp = 0, fn = 0, fp = 0;
@@ -108,6 +111,7 @@ __global__ void iou_counts_kernel(const unsigned long long* __restrict__ hist, i
 // tp / fn / fp of two boolean arrays of any length (vae_utility.py:57-59)
 __global__ void iou_pair_kernel(long long n, const uint8_t* __restrict__ g, const uint8_t* __restrict__ t,
                                 unsigned long long* __restrict__ counts) {
+    grid_dependency_sync();
     unsigned int tp = 0, fn = 0, fp = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const bool a = g[i] != 0, b = t[i] != 0;
@@ -137,7 +141,7 @@ extern "C" int cvae_iou_counts(int64_t n, const uint8_t* gt, const uint8_t* mask
     if (n == 0) return CVAE_OK;
     long long blocks = (n + 255) / 256;
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    iou_pair_kernel<<<(int)blocks, 256, 0, stream>>>(n, gt, mask, (unsigned long long*)counts3);
+    cvae::launch(iou_pair_kernel, (int)blocks, 256, 0, stream, n, gt, mask, (unsigned long long*)counts3);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -146,7 +150,7 @@ extern "C" int cvae_diff_grey(int frames, const float* recon_hi, const float* re
                               double* max_values, void* stream) {
     CVAE_REQUIRE(frames >= 0 && (frames == 0 || (recon_hi && recon_lo && diff && max_values)), CVAE_EINVAL, "diff_grey: bad argument");
     if (frames == 0) return CVAE_OK;
-    diff_grey_kernel<<<frames, 256, 0, (cudaStream_t)stream>>>(frames, recon_hi, recon_lo, diff, max_values);
+    cvae::launch(diff_grey_kernel, frames, 256, 0, (cudaStream_t)stream, frames, recon_hi, recon_lo, diff, max_values);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -160,12 +164,12 @@ extern "C" int cvae_mask_iou(int frames, const double* diff, const uint8_t* gt, 
     CVAE_CUDA(cudaMemsetAsync(hist512, 0, sizeof(uint64_t) * 512, stream));
     if (frames > 0) {
         int grid = frames < sm_count() * 6 ? frames : sm_count() * 6;
-        mask_iou_kernel<<<grid, 256, 0, stream>>>(frames, diff, gt, mean_max, diff_factor, thr, diff_u8, mask,
+        cvae::launch(mask_iou_kernel, grid, 256, 0, stream, frames, diff, gt, mean_max, diff_factor, thr, diff_u8, mask,
                                                   (unsigned long long*)hist512);
         CVAE_LAUNCH_CHECK();
     }
     if (nthr > 0) {
-        iou_counts_kernel<<<(nthr + 63) / 64, 64, 0, stream>>>((const unsigned long long*)hist512, nthr, thr_list, (long long*)counts);
+        cvae::launch(iou_counts_kernel, (nthr + 63) / 64, 64, 0, stream, (const unsigned long long*)hist512, nthr, thr_list, (long long*)counts);
         CVAE_LAUNCH_CHECK();
     }
     return CVAE_OK;

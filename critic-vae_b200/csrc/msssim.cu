@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(kMsThreads, 1)
 msssim_kernel(int planes, const float* __restrict__ recon, const float* __restrict__ x, const Window w,
               double* __restrict__ sums, const float* __restrict__ coef, const float* __restrict__ grad_out,
               float* __restrict__ d_recon) {
+    grid_dependency_sync();
     extern __shared__ float sm[];
     float* A = sm;                    // recon pyramid
     float* Bp = A + kPyr;             // target pyramid
@@ -277,6 +278,7 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
 __global__ void loss_finalize_kernel(int B, const float* __restrict__ ml, const double* __restrict__ kld_partial, int n_partial,
                                      const double* __restrict__ sums, float kld_weight, float* __restrict__ losses,
                                      float* __restrict__ coef) {
+    grid_dependency_sync();
     __shared__ double red[32];
     double acc = 0.0;
     if (kld_partial) {   // the latent kernel already reduced the KL term per 64 rows: add the partials in block order
@@ -316,6 +318,7 @@ __global__ void loss_finalize_kernel(int B, const float* __restrict__ ml, const 
 // dKLD/dmu = w mu / B, dKLD/dlogvar = w 0.5 (exp(lv) - 1) / B, times the upstream gradient
 __global__ void kld_bwd_kernel(int B, const float* __restrict__ ml, float kld_weight, const float* __restrict__ grad_out,
                                float* __restrict__ dmu, float* __restrict__ dlv) {
+    grid_dependency_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * 32) return;
     const int b = i >> 5, d = i & 31;
@@ -343,9 +346,9 @@ extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, cons
     CVAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 10, stream));
     const int planes = batch * 3;
     const int grid = planes < sm_count() ? planes : sm_count();
-    msssim_kernel<false><<<grid, kMsThreads, ms_smem(false), stream>>>(planes, recon, x, w, sums, nullptr, nullptr, nullptr);
+    cvae::launch(msssim_kernel<false>, grid, kMsThreads, ms_smem(false), stream, planes, recon, x, w, sums, nullptr, nullptr, nullptr);
     CVAE_LAUNCH_CHECK();
-    loss_finalize_kernel<<<1, kld_partial ? 32 : 1024, 0, stream>>>(batch, mu_logvar, kld_partial, (batch + 63) / 64, sums, kld_weight, losses, coef);
+    cvae::launch(loss_finalize_kernel, 1, kld_partial ? 32 : 1024, 0, stream, batch, mu_logvar, kld_partial, (batch + 63) / 64, sums, kld_weight, losses, coef);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -361,10 +364,10 @@ extern "C" int cvae_loss_bwd(int batch, const float* recon, const float* x, cons
     CVAE_OPT_IN_SMEM(msssim_kernel<true>, ms_smem(true));
     const int planes = batch * 3;
     const int grid = planes < sm_count() ? planes : sm_count();
-    msssim_kernel<true><<<grid, kMsThreads, ms_smem(true), stream>>>(planes, recon, x, w, nullptr, coef, grad_out, d_recon);
+    cvae::launch(msssim_kernel<true>, grid, kMsThreads, ms_smem(true), stream, planes, recon, x, w, nullptr, coef, grad_out, d_recon);
     CVAE_LAUNCH_CHECK();
     if (d_mu) {   // NULL, NULL: the caller folds the KL term's backward into cvae_latent_bwd (kld_grad_scale)
-        kld_bwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, stream>>>(batch, mu_logvar, kld_weight, grad_out, d_mu, d_logvar);
+        cvae::launch(kld_bwd_kernel, (batch * 32 + 255) / 256, 256, 0, stream, batch, mu_logvar, kld_weight, grad_out, d_mu, d_logvar);
         CVAE_LAUNCH_CHECK();
     }
     return CVAE_OK;

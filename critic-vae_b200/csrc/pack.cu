@@ -109,6 +109,7 @@ __device__ float pack_value(const cvae_pack_job& j, long long i, bool& is_bf16) 
 }
 
 __global__ void pack_weights_kernel(const PackJobs jobs) {
+    grid_dependency_sync();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < jobs.total;
          idx += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = jobs.count - 1;
@@ -159,7 +160,7 @@ extern "C" int cvae_pack_weights(const cvae_pack_job* jobs, int count, void* str
     const int threads = 256;
     long long blocks = (total + threads - 1) / threads;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    pack_weights_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(pj);
+    cvae::launch(pack_weights_kernel, (int)blocks, threads, 0, (cudaStream_t)stream, pj);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }

@@ -40,7 +40,8 @@ class WgradDesc(ctypes.Structure):
                 ("width", ctypes.c_int32), ("cout", ctypes.c_int32), ("cin", ctypes.c_int32),
                 ("splits", ctypes.c_int32),
                 ("x", c_void_p), ("dy", c_void_p), ("dy2", c_void_p), ("dw", c_void_p),
-                ("dbias", c_void_p), ("workspace", c_void_p), ("fold_stream", c_void_p)]
+                ("dbias", c_void_p), ("workspace", c_void_p), ("fold_stream", c_void_p),
+                ("workspace_bytes", ctypes.c_int64)]
 
 
 lib.cvae_last_error.restype = ctypes.c_char_p
@@ -76,6 +77,7 @@ _SIGS = {
     "cvae_pack_weights": ([ctypes.POINTER(PackJob), c_int, P], c_int),
     "cvae_bn_finalize": ([c_int, c_i64, c_int, P, P, P, P, P, P, P, c_float, c_float, P, P], c_int),
     "cvae_bn_pool_act_fwd": ([c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P], c_int),
+    "cvae_bn_fwd": ([c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_float, c_float, P, P, P, P, P], c_int),
     "cvae_bn_pool_act_bwd": ([c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P], c_int),
     "cvae_fc_fwd": ([c_int, P, P, P, P, P, P], c_int),
     "cvae_fc_bwd": ([c_int, P, P, P, P, P, P, P, P, P], c_int),
@@ -88,6 +90,11 @@ _SIGS = {
     "cvae_loss_bwd": ([c_int, P, P, P, ctypes.POINTER(c_float), c_float, P, P, P, P, P, P], c_int),
     "cvae_adam_step": ([c_i64, P, P, P, P, P, c_float, c_float, c_float, c_float, c_float, P], c_int),
     "cvae_critic_param_count": ([], c_int),
+    "cvae_comm_unique_id": ([P], c_int),
+    "cvae_comm_init": ([c_int, c_int, P], c_int),
+    "cvae_comm_world": ([], c_int),
+    "cvae_comm_allreduce_sum": ([P, c_i64, P], c_int),
+    "cvae_comm_destroy": ([], c_int),
     "cvae_launch_count": ([], c_i64),
     "cvae_iou_counts": ([c_i64, P, P, P, P], c_int),
     "cvae_frames_u8_to_f32": ([c_int, P, P, P], c_int),

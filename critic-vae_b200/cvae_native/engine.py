@@ -293,14 +293,12 @@ class VAEEngine:
                            epilogue=L.EPI_STATS, ktab=L.KTAB_GENERIC, src=ws.a[i - 1], wpack=self.packed[f"E{i}f"],
                            out=ws.c[i], stats=stats)
             cname, bname = f"encoder.model.{ENC_CONV_IDX[i]}", f"encoder.model.{ENC_BN_IDX[i]}"
-            L.check(L.lib.cvae_bn_finalize(co, B * h * h, int(training), _ptr(stats), _ptr(self.view(bname + ".weight")),
-                                           _ptr(self.view(bname + ".bias")), _ptr(self.view(cname + ".bias")),
-                                           _ptr(self.running_mean[i]), _ptr(self.running_var[i]), _ptr(self.nbt[i]),
-                                           BN_MOMENTUM, BN_EPS, _ptr(ws.ss[i]), s))
             save = training and hasattr(ws, "xh")
-            L.check(L.lib.cvae_bn_pool_act_fwd(B, h, h, co, L.ACT_TANH if i == 3 else L.ACT_RELU, _ptr(ws.c[i]),
-                                               _ptr(ws.ss[i]), _ptr(ws.a[i]), _ptr(ws.xh[i]) if save else None,
-                                               _ptr(ws.am[i]) if save else None, s))
+            # BatchNorm finalize + normalise + 2x2 max-pool + activation in one launch
+            L.check(L.lib.cvae_bn_fwd(B, h, h, co, L.ACT_TANH if i == 3 else L.ACT_RELU, int(training), _ptr(ws.c[i]), _ptr(stats),
+                                      _ptr(self.view(bname + ".weight")), _ptr(self.view(bname + ".bias")), _ptr(self.view(cname + ".bias")),
+                                      _ptr(self.running_mean[i]), _ptr(self.running_var[i]), _ptr(self.nbt[i]), BN_MOMENTUM, BN_EPS,
+                                      _ptr(ws.ss[i]), _ptr(ws.a[i]), _ptr(ws.xh[i]) if save else None, _ptr(ws.am[i]) if save else None, s))
         L.check(L.lib.cvae_fc_fwd(B, _ptr(ws.a[3]), _ptr(self.packed["fc"]), _ptr(self.view("encoder.fc_mu.bias")),
                                   _ptr(self.view("encoder.fc_var.bias")), _ptr(ws.ml), s))
         return ws.ml
@@ -350,6 +348,9 @@ class VAEEngine:
     # ---- backward -----------------------------------------------------------------------------
     def _wgrad(self, g, name, **kw):
         d = L.WgradDesc(**{k: (_ptr(v) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
+        # A conv bias in front of BatchNorm has an exactly-zero gradient (the batch mean removes it): leave
+        # the zero-initialised slot of the flat buffer untouched instead of writing rounding noise.
+        d.dbias = None if name.startswith("encoder.") else _ptr(self.view(name + ".bias", g))
         need = int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d)))
         # one split-K workspace per layer: the fold of one layer overlaps the GEMM of the next
         ws = self._wgrad_ws.get(name) if isinstance(self._wgrad_ws, dict) else None
@@ -357,10 +358,7 @@ class VAEEngine:
             if not isinstance(self._wgrad_ws, dict):
                 self._wgrad_ws = {}
             ws = self._wgrad_ws[name] = torch.empty(need, dtype=torch.uint8, device=self.device)
-        # A conv bias in front of BatchNorm has an exactly-zero gradient (the batch mean removes it): leave
-        # the zero-initialised slot of the flat buffer untouched instead of writing rounding noise.
-        d.dw, d.workspace = _ptr(self.view(name + ".weight", g)), _ptr(ws)
-        d.dbias = None if name.startswith("encoder.") else _ptr(self.view(name + ".bias", g))
+        d.dw, d.workspace, d.workspace_bytes = _ptr(self.view(name + ".weight", g)), _ptr(ws), ws.numel()
         if self.side_stream is None or self.profile is not None:
             self._timed("conv_wgrad", lambda: L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr())))
             return

@@ -15,6 +15,7 @@ libcvae.so.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
@@ -68,6 +69,20 @@ class TrainStep:
         if self.overlap:
             self.comm_stream = torch.cuda.Stream()
             self.early_event = torch.cuda.Event(external=True)
+        # CVAE_COMM=native: the all-reduce goes through libcvae's own NCCL communicator (cvae_comm_*, csrc/comm.cu), the path a
+        # non-Python host would use; torch.distributed then only carries the 128 rendezvous bytes.  Default: torch.distributed.
+        self.native_comm = self.world > 1 and os.environ.get("CVAE_COMM") == "native"
+        if self.native_comm and L.lib.cvae_comm_world() == 0:
+            rank = torch.distributed.get_rank(process_group)
+            ident = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (ctypes.c_char * 128)()
+                L.check(L.lib.cvae_comm_unique_id(buf))
+                ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            ident = ident.to(dev)
+            torch.distributed.broadcast(ident, src=torch.distributed.get_global_rank(process_group, 0), group=process_group)
+            raw = bytes(ident.cpu().numpy().tobytes())
+            L.check(L.lib.cvae_comm_init(rank, self.world, raw))
 
     # ---- the work ---------------------------------------------------------------------------------
     def _front(self, from_u8, stage="all"):
@@ -114,7 +129,19 @@ class TrainStep:
         on the communication stream as soon as the event inside the backward pass fires (beside the encoder's backward
         pass), the late bucket behind the whole pass; the current stream then waits for both."""
         early, late = self._buckets()
-        if self.overlap:
+        if self.native_comm:
+            reduce_ = lambda t: L.check(L.lib.cvae_comm_allreduce_sum(t.data_ptr(), t.numel(), L.stream_ptr()))
+            if self.overlap:
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(self.early_event)
+                    reduce_(early)
+                    done = torch.cuda.Event()
+                    done.record()
+                reduce_(late)
+                torch.cuda.current_stream().wait_event(done)
+            else:
+                reduce_(self.eng.gflat)
+        elif self.overlap:
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(self.early_event)
                 w1 = torch.distributed.all_reduce(early, group=self.pg, async_op=True)

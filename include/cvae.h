@@ -124,8 +124,12 @@ typedef struct {
     void* workspace;             /* >= cvae_conv_wgrad_workspace_bytes(d) */
     void* fold_stream;           /* optional second stream for the partial-sum fold (NULL: same stream); the fold is
                                     ordered after the GEMM with an event, the caller joins fold_stream itself */
+    int64_t workspace_bytes;     /* size of `workspace`; the call fails with CVAE_EINVAL instead of writing past it
+                                    (0 = unchecked) */
 } cvae_wgrad_desc;
 
+/* Bytes of split-K workspace cvae_conv_wgrad needs for this shape.  Only kind / batch / height / width / cout / cin /
+ * splits are read; the figure covers the call with and without a bias gradient. */
 int64_t cvae_conv_wgrad_workspace_bytes(const cvae_wgrad_desc* d);
 /* profiling aid: device buffer of >= 8 * (CTAs of the launch) uint64 cycle counters (NULL = off) */
 void cvae_wgrad_debug_counters(void* device_buf);
@@ -178,6 +182,12 @@ int cvae_bn_finalize(int channels, int64_t count, int training, const double* st
  * neither (NULL, NULL in evaluation). */
 int cvae_bn_pool_act_fwd(int batch, int height, int width, int channels, int act, const void* conv_out,
                          const float* scale_shift, void* out, void* xhat_max, void* argmax, void* stream);
+/* cvae_bn_finalize + cvae_bn_pool_act_fwd in one launch (count = batch * height * width; channels <= 256): every CTA
+ * derives the scale / shift itself, block 0 publishes scale_shift and updates the running buffers. */
+int cvae_bn_fwd(int batch, int height, int width, int channels, int act, int training, const void* conv_out,
+                const double* stats, const float* gamma, const float* beta, const float* conv_bias, float* running_mean,
+                float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* scale_shift, void* out,
+                void* xhat_max, void* argmax, void* stream);
 /* conv_out bf16 [B][H][W][C]; act_out, d_act, xhat_max bf16 [B][H/2][W/2][C]; argmax as above; sums: [2][C]
  * double scratch; d_conv bf16 [B][H][W][C]; dgamma, dbeta fp32 [C] (overwritten). */
 int cvae_bn_pool_act_bwd(int batch, int height, int width, int channels, int act, const void* conv_out,
@@ -240,6 +250,19 @@ int cvae_loss_bwd(int batch, const float* recon, const float* x, const float* mu
  * ---------------------------------------------------------------------------------------------- */
 int cvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                    int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel training (the reference is single-GPU): NCCL all-reduce of the flat
+ * gradient behind the C ABI, one communicator per process = per GPU, bound to libnccl.so.2 at run
+ * time.  Rank 0 creates 128 id bytes, the host ships them to every rank (any transport), every rank
+ * calls cvae_comm_init (a collective), then cvae_comm_allreduce_sum sums `count` floats in place,
+ * asynchronously on `stream`; cvae_adam_step's grad_scale = 1 / world turns the sum into the mean.
+ * ---------------------------------------------------------------------------------------------- */
+int cvae_comm_unique_id(void* id128);
+int cvae_comm_init(int rank, int world, const void* id128);
+int cvae_comm_world(void);
+int cvae_comm_allreduce_sum(float* buf, int64_t count, void* stream);
+int cvae_comm_destroy(void);
 
 /* uint8 HWC frames [N][64][64][3] -> fp32 NCHW [N][3][64][64] = astype(float32) / 255, the
  * preprocessing of vae_utility.py:324-343 (adjust_values + HWC->CHW) done on the device. */

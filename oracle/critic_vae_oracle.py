@@ -118,6 +118,18 @@ def msssim_window_2d(channels=3) -> torch.Tensor:
     return g.mm(g.t()).float()[None, None].expand(channels, 1, 11, 11).contiguous()
 
 
+_MSSSIM_CONST = {}
+
+
+def _msssim_constants(channels, device):
+    """(window, level weights) on `device`, built once per device: bench.py's gpu_baseline leg captures the step in a
+    CUDA graph, where a host-to-device copy of a fresh constant is not allowed."""
+    key = (channels, str(device))
+    if key not in _MSSSIM_CONST:
+        _MSSSIM_CONST[key] = (msssim_window_2d(channels).to(device), torch.tensor(MSSSIM_WEIGHTS, dtype=torch.float32).to(device))
+    return _MSSSIM_CONST[key]
+
+
 def ssim_level(a, b, win):
     """vae_nets.py:181-215 with size_average=True: returns (ssim mean, cs mean) over all of B,3,H,W."""
     c = a.shape[1]
@@ -136,8 +148,7 @@ def ssim_level(a, b, win):
 
 def msssim_loss(recon, x):
     """vae_nets.py:217-247: 1 - prod_{l<4}( cs_l^w_l * ssim_4^w_4 )."""
-    win = msssim_window_2d(recon.shape[1]).to(recon.device)     # (device-agnostic: bench.py's gpu_baseline leg runs this on cuda)
-    w = torch.tensor(MSSSIM_WEIGHTS, dtype=torch.float32, device=recon.device)
+    win, w = _msssim_constants(recon.shape[1], recon.device)
     a, b = recon, x
     ss, cs = [], []
     for _ in range(5):
@@ -151,7 +162,7 @@ def msssim_loss(recon, x):
 
 def msssim_level_means(recon, x):
     """The ten batch-global means (ssim_l, cs_l) of vae_nets.py:224-236, for kernel-level checks."""
-    win = msssim_window_2d(recon.shape[1]).to(recon.device)
+    win, _ = _msssim_constants(recon.shape[1], recon.device)
     a, b = recon, x
     out = []
     for _ in range(5):

@@ -14,10 +14,14 @@ pytestmark = pytest.mark.gpu
 def run_wgrad(L, kind, B, H, W, cout, cin, x, dy, dy2=None, splits=0):
     d = L.WgradDesc(kind=kind, batch=B, height=H, width=W, cout=cout, cin=cin, splits=splits,
                     x=x.data_ptr(), dy=dy.data_ptr(), dy2=dy2.data_ptr() if dy2 is not None else None)
-    ws = torch.empty(int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d))), dtype=torch.uint8, device="cuda")
     dw = torch.full((cout, cin, 5, 5), float("nan"), device="cuda")
     db = torch.full((cout,), float("nan"), device="cuda")
-    d.dw, d.dbias, d.workspace = dw.data_ptr(), db.data_ptr(), ws.data_ptr()
+    d.dw, d.dbias = dw.data_ptr(), db.data_ptr()
+    # the split-K partials live in the workspace: poison it (a partial the fold reads but no CTA wrote shows up as NaN) and tell
+    # the library its size (a call that would write past it fails instead)
+    need = int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d)))
+    ws = torch.full((need // 4,), float("nan"), device="cuda")
+    d.workspace, d.workspace_bytes = ws.data_ptr(), need
     L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()))
     torch.cuda.synchronize()
     L.check(L.lib.cvae_check_device_fault(L.stream_ptr()))
@@ -33,7 +37,9 @@ def _check(dw, db, ref_w, ref_b):
 @pytest.mark.parametrize("B,Cin,Cout,HW,splits", [(3, 32, 64, 32, 0), (4, 64, 128, 16, 0), (5, 128, 256, 8, 0),
                                                  (6, 256, 128, 4, 0), (3, 32, 64, 32, 1), (7, 64, 128, 16, 3),
                                                  # TMA-fed variant: several chunks per CTA, image boxes running past the batch
-                                                 (41, 128, 256, 8, 0), (33, 64, 128, 16, 0), (50, 256, 128, 4, 0)])
+                                                 (41, 128, 256, 8, 0), (33, 64, 128, 16, 0), (50, 256, 128, 4, 0),
+                                                 # tap-stacked variant (32 -> 64 channels): many chunks per CTA, other map sizes, forced splits
+                                                 (37, 32, 64, 32, 0), (5, 32, 64, 16, 0), (9, 32, 64, 8, 7), (150, 32, 64, 4, 0)])
 def test_wgrad_5x5(B, Cin, Cout, HW, splits):
     L = _native()
     x, dy = rb(_rand((B, Cin, HW, HW), 31)), rb(_rand((B, Cout, HW, HW), 32))
@@ -42,7 +48,8 @@ def test_wgrad_5x5(B, Cin, Cout, HW, splits):
     _check(dw, db, ref_w, dy.double().sum((0, 2, 3)).float())
 
 
-@pytest.mark.parametrize("B,Cin,Cout,HW", [(3, 128, 64, 4), (3, 64, 32, 8), (2, 32, 32, 16), (45, 128, 64, 4)])
+@pytest.mark.parametrize("B,Cin,Cout,HW", [(3, 128, 64, 4), (3, 64, 32, 8), (2, 32, 32, 16), (45, 128, 64, 4),
+                                           (21, 32, 32, 16), (5, 32, 32, 8), (40, 32, 32, 32)])      # tap-stacked variant (32 -> 4 x 32)
 def test_wgrad_upsample_folded(B, Cin, Cout, HW):
     L = _native()
     x, dy = rb(_rand((B, Cin, HW, HW), 33)), rb(_rand((B, Cout, 2 * HW, 2 * HW), 34))
@@ -74,3 +81,22 @@ def test_wgrad_decoder_last_conv(B):
     (y * dy.double()).sum().backward()
     dw, db = run_wgrad(L, L.WGRAD_SHIFT_PHASE12, B, 32, 32, 3, 32, nhwc_bf16(x), g.cuda(), dy2=recon.cuda())
     _check(dw, db, Wt.grad.float(), dy.double().sum((0, 2, 3)).float())
+
+
+def test_wgrad_refuses_a_workspace_that_is_too_small():
+    """The engine once sized the workspace before it filled in dbias (the bias pseudo-group makes the partials larger): the
+    descriptor now carries the size and the call fails instead of writing past the end; the query covers both forms."""
+    L = _native()
+    B, Cin, Cout, HW = 5, 128, 256, 8
+    x, dy = nhwc_bf16(_rand((B, Cin, HW, HW), 1)), nhwc_bf16(_rand((B, Cout, HW, HW), 2))
+    dw, db = torch.zeros(Cout, Cin, 5, 5, device="cuda"), torch.zeros(Cout, device="cuda")
+    d = L.WgradDesc(kind=L.WGRAD_5X5, batch=B, height=HW, width=HW, cout=Cout, cin=Cin, splits=0, x=x.data_ptr(), dy=dy.data_ptr(), dw=dw.data_ptr())
+    without_bias = int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d)))
+    d.dbias = db.data_ptr()
+    assert int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d))) == without_bias      # one answer for both forms
+    ws = torch.empty(without_bias, dtype=torch.uint8, device="cuda")
+    d.workspace, d.workspace_bytes = ws.data_ptr(), 25 * Cout * Cin * 4      # one split without the bias block: too small
+    assert L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()) == -1 and b"workspace" in L.lib.cvae_last_error()
+    d.workspace_bytes = without_bias
+    L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()))
+    torch.cuda.synchronize()

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B = 32
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, comm):
     for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "critic-vae_b200")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -26,7 +26,7 @@ def _worker(rank, world, port, out_dir):
     import synth
     from test_vae_module import _modules
     from cvae_native.trainer import TrainStep
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NCCL_IB_DISABLE="1", NCCL_P2P_LEVEL="NVL")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NCCL_IB_DISABLE="1", NCCL_P2P_LEVEL="NVL", CVAE_COMM=comm)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     crit = torch.load(os.path.join(ROOT, "critic-vae_b200", "saved-networks",
@@ -45,10 +45,15 @@ def _worker(rank, world, port, out_dir):
     torch.save({"flat0": flat0.cpu(), "flat": st.eng.flat.cpu(), "gsum": st.eng.gflat.cpu(), "losses": losses.cpu()},
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
+    if comm == "native":
+        from cvae_native import binding as L
+        assert L.lib.cvae_comm_world() == world, "CVAE_COMM=native must have built libcvae's own communicator"
+        L.check(L.lib.cvae_comm_destroy())
     dist.destroy_process_group()
 
 
-def test_two_rank_step_equals_oracle_on_the_shards(tmp_path, critic_state):
+@pytest.mark.parametrize("comm", ["torch", "native"])      # torch.distributed's all-reduce / libcvae's cvae_comm_allreduce_sum
+def test_two_rank_step_equals_oracle_on_the_shards(tmp_path, critic_state, comm):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -59,7 +64,7 @@ def test_two_rank_step_equals_oracle_on_the_shards(tmp_path, critic_state):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     world = 2
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), comm), nprocs=world, join=True)
     r = [torch.load(os.path.join(tmp_path, f"rank{k}.pt")) for k in range(world)]
     assert torch.equal(r[0]["flat0"], r[1]["flat0"]), "TrainStep must broadcast rank 0's parameters"
     assert torch.equal(r[0]["flat"], r[1]["flat"]), "ranks diverged after the step"

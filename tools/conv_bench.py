@@ -9,7 +9,7 @@ import torch
 from cvae_native import binding as L
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-B = int(args[0]) if args else 256
+B = int(args[0]) if args and args[0].isdigit() else 256
 SWEEP = "--sweep" in sys.argv
 WA = "--wa" in sys.argv          # run the layers the weights-as-A kernel covers through it (CVAE_KTAB_BLOCK64)
 WA_LAYERS = {"E1f": (32, 2), "E2f": (64, 1), "E3f": (64, 1), "D0f": (64, 1), "D1f": (64, 1), "D2f": (64, 1), "D3f": (32, 1),

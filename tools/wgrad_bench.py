@@ -7,7 +7,8 @@ for p in ("tests", "critic-vae_b200"):
 import torch
 from cvae_native import binding as L
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 256
+ONLY = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
 dev, bf = "cuda", torch.bfloat16
 # name, kind, H (grid of the GEMM's K pixels), cin, cout
 LAYERS = [("E0w", L.WGRAD_SHIFT_FRAMES, 64, 3, 32), ("E1w", L.WGRAD_5X5, 32, 32, 64), ("E2w", L.WGRAD_5X5, 16, 64, 128),
@@ -16,6 +17,8 @@ LAYERS = [("E0w", L.WGRAD_SHIFT_FRAMES, 64, 3, 32), ("E1w", L.WGRAD_5X5, 32, 32,
 ws = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
 tot = 0.0
 for name, kind, H, cin, cout in LAYERS:
+    if ONLY and name not in ONLY:
+        continue
     if kind == L.WGRAD_SHIFT_FRAMES:
         x = torch.rand(B, 3, H, H, device=dev); dy = torch.randn(B, H, H, cout, device=dev).to(bf); dy2 = None
     elif kind == L.WGRAD_5X5:
