@@ -11,7 +11,9 @@ One "step" = the reference's training iteration (vae.py:47-58) on one synthetic 
 VAE (tests/synth.py seed 0), the shipped critic checkpoint.  Prints ONE JSON line (rank 0).
 """
 import argparse
+import functools
 import json
+import operator
 import os
 import subprocess
 import sys
@@ -299,8 +301,15 @@ def gpu_baseline(device, batch, steps=20, warmup=5):
                         if graphed:
                             side.synchronize()
                             g = torch.cuda.CUDAGraph()
-                            with torch.cuda.graph(g, stream=side):
-                                loss = step()
+                            # torch.prod's backward looks for zeros on the host (a sync, illegal during capture): for the graphed
+                            # variants the 4-element product of the MS-SSIM levels is spelled out as multiplications
+                            orig_prod = torch.prod
+                            torch.prod = lambda t, *a, **k: functools.reduce(operator.mul, t.unbind(0)) if not a and not k and t.dim() == 1 else orig_prod(t, *a, **k)
+                            try:
+                                with torch.cuda.graph(g, stream=side):
+                                    loss = step()
+                            finally:
+                                torch.prod = orig_prod
                             fn = g.replay
                             fn()
                         side.synchronize()

@@ -331,10 +331,16 @@ __device__ __forceinline__ void mma_role_pair8(const ConvArgs& a, PipeBars& bars
     const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (256u >> 4) | (1u << 14);
     const uint32_t b_lo0 = ((wring_addr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
     uint32_t it = 0;
+    const bool prof = a.dbg != nullptr;
+    long long t0 = 0, tq = 0, t_acc = 0, t_pl = 0;
+    if (prof) t0 = clock64();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const uint32_t ab = it & 1u, buf = it & 1u;
+        if (prof) tq = clock64();
         mbar_wait(&bars.acc_empty[ab], ((it >> 1) & 1u) ^ 1u, a.fault);
+        if (prof) { t_acc += clock64() - tq; tq = clock64(); }
         mbar_wait(&bars.p_full[buf], (it >> 1) & 1u, a.fault);
+        if (prof) t_pl += clock64() - tq;
         if (it == 0) mbar_wait(&bars.w_full[0], 0, a.fault);
         tc_fence_after();
         const uint32_t acc = tmem_base + ab * (uint32_t)(TM * N);
@@ -354,6 +360,10 @@ __device__ __forceinline__ void mma_role_pair8(const ConvArgs& a, PipeBars& bars
         }
         umma_commit(&bars.p_empty[buf]);
         umma_commit(&bars.acc_full[ab]);
+    }
+    if (prof) {
+        unsigned long long* o = a.dbg + (size_t)blockIdx.x * 8;
+        o[0] = (unsigned long long)(clock64() - t0); o[1] = t_acc; o[2] = t_pl; o[3] = 0; o[4] = it;
     }
 }
 
@@ -529,7 +539,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvAr
                         fill_planes_async<LOADER>(a.ps, a.dPW, a.dIH, pbuf + (size_t)buf * a.buf_bytes, a.plane_stride, v0 - a.halo, a.L,
                                                   cg * a.planes, a.planes, ptid, kProducerThreads);
                     else   // fp32 NCHW sources are converted by the producer threads themselves
-                        fill_planes<LOADER>(a.ps, pbuf + (size_t)buf * a.buf_bytes, a.plane_stride, v0 - a.halo, a.L, ptid, kProducerThreads);
+                        fill_planes<LOADER>(a.ps, a.dPW, a.dIH, pbuf + (size_t)buf * a.buf_bytes, a.plane_stride, v0 - a.halo, a.L, ptid, kProducerThreads);
                 }
                 cp_async_wait_all();
                 fence_proxy_async();

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradAr
             if constexpr (kAsyncA)
                 fill_planes_async<LA>(a.pa, a.dPW, a.dIH, A, a.stride_a, c0 + a.a_first, a.a_count, mb * 16, a.a_planes_cta, tid, kWgLoaders);
             fill_planes_async<LB>(a.pb, a.dPW, a.dIH, Bp, a.stride_b, c0 + a.b_first, a.b_count, 0, a.pb.planes, tid, kWgLoaders);
-            if constexpr (!kAsyncA) fill_planes<LA>(a.pa, A, a.stride_a, c0 + a.a_first, a.a_count, tid, kWgLoaders);
+            if constexpr (!kAsyncA) fill_planes<LA>(a.pa, a.dPW, a.dIH, A, a.stride_a, c0 + a.a_first, a.a_count, tid, kWgLoaders);
             if (prof) { const long long t = clock64(); t_issue += t - tq; tq = t; }
             cp_async_wait_all();
             fence_proxy_async();
@@ -849,8 +849,7 @@ static int launch_wgrad_stack(const cvae_wgrad_desc* d, int H, int W, int pad, c
             if (!plan(pw, RA)) continue;
             const int per_cta = (t.num_chunks + splits - 1) / splits;
             double cost = (double)per_cta * (t.kc + 64);          // K per CTA plus a per-chunk overhead worth ~64 pixels
-            if (t.nbuf < 3) cost *= 1.15;
-            if (per_cta < 2) cost *= 2.0;
+            if (per_cta < 2) cost *= 2.0;                          // (measured, profiles/r02_wgrad_stack_sweep.log: two buffers are enough here)
             if (cost < best_cost) { best_cost = cost; best_pw = pw; best_ra = RA; }
         }
     if (g_wg_stack_pw > 0 && g_wg_stack_ra > 0 && plan(W + pad + g_wg_stack_pw - 1, g_wg_stack_ra)) { best_pw = W + pad + g_wg_stack_pw - 1; best_ra = g_wg_stack_ra; }

@@ -392,14 +392,29 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
     const float bc1 = (float)(1.0 - pow((double)b1, t));
     const float sq_bc2 = (float)sqrt(1.0 - pow((double)b2, t));
     const float step_size = lr / bc1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float gr = g[i] * grad_scale;
-        const float mi = m[i] + (1.f - b1) * (gr - m[i]);           // lerp form used by torch
-        const float vi = v[i] * b2 + (1.f - b2) * gr * gr;
-        m[i] = mi;
-        v[i] = vi;
+    auto update = [&](float& pi, float gi, float& mi, float& vi) {
+        const float gr = gi * grad_scale;
+        mi = mi + (1.f - b1) * (gr - mi);                          // lerp form used by torch
+        vi = vi * b2 + (1.f - b2) * gr * gr;
         const float denom = sqrtf(vi) / sq_bc2 + eps;
-        p[i] = p[i] - step_size * (mi / denom);
+        pi = pi - step_size * (mi / denom);
+    };
+    // float4 body (the flat buffers are 16-byte aligned), scalar tail of n % 4 elements in the last thread's wake
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        const float4 gv = reinterpret_cast<const float4*>(g)[i];
+        update(pv.x, gv.x, mv.x, vv.x);
+        update(pv.y, gv.y, mv.y, vv.y);
+        update(pv.z, gv.z, mv.z, vv.z);
+        update(pv.w, gv.w, mv.w, vv.w);
+        reinterpret_cast<float4*>(p)[i] = pv;
+        reinterpret_cast<float4*>(m)[i] = mv;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
+        const long long i = (n4 << 2) + threadIdx.x;
+        update(p[i], g[i], m[i], v[i]);
     }
 }
 __global__ void adam_tick_kernel(long long* step) {
@@ -540,7 +555,9 @@ extern "C" int cvae_adam_step(int64_t n, float* params, const float* grads, floa
                               int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale,
                               void* stream) {
     CVAE_REQUIRE(n > 0 && params && grads && exp_avg && exp_avg_sq && step, CVAE_EINVAL, "adam_step: bad argument");
-    cvae::launch(adam_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq,
+    CVAE_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, CVAE_EINVAL,
+                 "adam_step: the flat buffers must be 16-byte aligned");
+    cvae::launch(adam_kernel, grid_for((n + 3) / 4, 256, 16), 256, 0, (cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq,
                                                                     (const long long*)step, lr, beta1, beta2, eps, grad_scale);
     CVAE_LAUNCH_CHECK();
     cvae::launch(adam_tick_kernel, 1, 1, 0, (cudaStream_t)stream, (long long*)step);

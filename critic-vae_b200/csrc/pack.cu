@@ -33,8 +33,11 @@ __device__ __forceinline__ float phase_weight(const float* W, int cin, int co, i
     return acc;
 }
 
-__device__ float pack_value(const cvae_pack_job& j, long long i, bool& is_bf16) {
+// Value of element i = i0 + e of job j.  The bf16 layouts all have the 8 channels of one core-matrix row as their fastest
+// index (e), so the kernel calls this in an unrolled loop over e and the compiler hoists everything that depends on i0 only.
+__device__ __forceinline__ float pack_value(const cvae_pack_job& j, long long i0, int e, bool& is_bf16) {
     const float* W = (const float*)j.src;
+    const long long i = i0 + e;
     is_bf16 = true;
     if (j.kind == CVAE_PACK_FC) {         // dst fp32 [4096 k'][64]: k' = p*256 + c  <->  k = c*16 + p
         is_bf16 = false;
@@ -50,9 +53,9 @@ __device__ float pack_value(const cvae_pack_job& j, long long i, bool& is_bf16) 
     }
     // UMMA K-major blocks: [nb][kstep][n/8][kchunk 2][row 8][elem 8]
     const int N = j.n, NB = N < 128 ? N : 128;
-    const int e = (int)(i & 7), r = (int)((i >> 3) & 7), kc = (int)((i >> 6) & 1);
-    const int ng = (int)((i >> 7) % (NB / 8));
-    const long long rest = i / (16LL * NB);
+    const int r = (int)((i0 >> 3) & 7), kc = (int)((i0 >> 6) & 1);
+    const int ng = (int)((i0 >> 7) % (NB / 8));
+    const long long rest = i0 / (16LL * NB);
     const int ks = (int)(rest % j.ksteps), nb = (int)(rest / j.ksteps);
     int n = nb * NB + ng * 8 + r;
     const int k16 = kc * 8 + e;
@@ -110,19 +113,29 @@ __device__ float pack_value(const cvae_pack_job& j, long long i, bool& is_bf16) 
 
 __global__ void pack_weights_kernel(const PackJobs jobs) {
     grid_dependency_sync();
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < jobs.total;
-         idx += (long long)gridDim.x * blockDim.x) {
+    // one thread = 8 consecutive elements (every job's element count is a multiple of 8): one index decode, one 16-byte store
+    for (long long idx8 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx8 * 8 < jobs.total;
+         idx8 += (long long)gridDim.x * blockDim.x) {
+        const long long idx = idx8 * 8;
         int lo = 0, hi = jobs.count - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
             if (jobs.start[mid] <= idx) lo = mid; else hi = mid - 1;
         }
         const cvae_pack_job& j = jobs.job[lo];
-        const long long i = idx - jobs.start[lo];
-        bool is_bf16;
-        const float v = pack_value(j, i, is_bf16);
-        if (is_bf16) ((__nv_bfloat16*)j.dst)[i] = __float2bfloat16_rn(v);
-        else ((float*)j.dst)[i] = v;
+        const long long i0 = idx - jobs.start[lo];
+        bool is_bf16 = true;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = pack_value(j, i0, e, is_bf16);
+        if (is_bf16) {
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)j.dst + i0) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        } else {
+            float4* o = reinterpret_cast<float4*>((float*)j.dst + i0);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
     }
 }
 
@@ -157,8 +170,9 @@ extern "C" int cvae_pack_weights(const cvae_pack_job* jobs, int count, void* str
     }
     pj.start[count] = total;
     pj.total = total;
+    CVAE_REQUIRE(total % 8 == 0, CVAE_EINVAL, "pack_weights: element counts must be multiples of 8");
     const int threads = 256;
-    long long blocks = (total + threads - 1) / threads;
+    long long blocks = (total / 8 + threads - 1) / threads;
     if (blocks > 148 * 16) blocks = 148 * 16;
     cvae::launch(pack_weights_kernel, (int)blocks, threads, 0, (cudaStream_t)stream, pj);
     CVAE_LAUNCH_CHECK();

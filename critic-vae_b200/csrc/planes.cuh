@@ -114,9 +114,47 @@ __device__ __forceinline__ void fill_planes_async(const PlaneSrc& a, const FastD
 // Synchronous plane fill for the two fp32 NCHW sources (the threads convert to bf16 themselves); the bf16 sources go
 // through fill_planes_async.
 template <int LOADER>
-__device__ __forceinline__ void fill_planes(const PlaneSrc& a, uint8_t* planes, int plane_stride,
+__device__ __forceinline__ void fill_planes(const PlaneSrc& a, const FastDiv& dPW, const FastDiv& dIH, uint8_t* planes, int plane_stride,
                                             int v_first, int count, int tid, int nthreads) {
     static_assert(LOADER == CVAE_LOAD_NCHW3 || LOADER == CVAE_LOAD_S2D_NCHW3_DTANH, "bf16 sources use fill_planes_async");
+    if constexpr (LOADER == CVAE_LOAD_NCHW3) {
+        // Batches of kBatch pixels per thread: all 3 * kBatch loads are issued before the first value is used, so a
+        // batch costs one global-memory latency instead of kBatch (the producer was the limiter of encoder conv 0:
+        // ~960 cycles per pixel pair with the loads two deep, profiles/r02_e0f_producer.log).
+        constexpr int kBatch = 8;
+        const size_t cs = (size_t)a.H * a.W;
+        const float c3 = a.ones ? 1.f : 0.f;
+        for (int j0 = tid; j0 < count; j0 += kBatch * nthreads) {
+            float f[kBatch][3];
+            bool ok[kBatch];
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+                const int j = j0 + q * nthreads;
+                const int v = v_first + j;
+                ok[q] = false;
+                f[q][0] = f[q][1] = f[q][2] = 0.f;
+                if (j < count && v >= 0) {
+                    const uint32_t vrow = fast_div((uint32_t)v, dPW);
+                    const int vcol = (int)((uint32_t)v - vrow * (uint32_t)a.PW);
+                    const int n = (int)fast_div(vrow, dIH);
+                    const int r = (int)(vrow - (uint32_t)n * (uint32_t)a.IH);
+                    if ((vcol < a.W) && (r >= a.pad) && (n < a.B)) {
+                        const float* s = reinterpret_cast<const float*>(a.src) + ((size_t)n * 3 * a.H + (r - a.pad)) * a.W + vcol;
+                        f[q][0] = __ldg(s);
+                        f[q][1] = __ldg(s + cs);
+                        f[q][2] = __ldg(s + 2 * cs);
+                    }
+                }
+                ok[q] = j < count;
+            }
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q)
+                if (ok[q])
+                    *reinterpret_cast<uint4*>(planes + (size_t)(j0 + q * nthreads) * 16) =
+                        make_uint4(pack_bf16x2(f[q][0], f[q][1]), pack_bf16x2(f[q][2], c3), 0u, 0u);
+        }
+        return;
+    }
 #pragma unroll 2
     for (int j = tid; j < count; j += nthreads) {
         const int v = v_first + j;
@@ -128,17 +166,6 @@ __device__ __forceinline__ void fill_planes(const PlaneSrc& a, uint8_t* planes, 
         const int h = r - a.pad, w = vcol;
         uint8_t* dst = planes + (size_t)j * 16;
         if constexpr (LOADER == CVAE_LOAD_NCHW3) {
-            uint4 val = make_uint4(0, 0, 0, 0);
-            float c3 = a.ones ? 1.f : 0.f;
-            if (valid) {
-                const float* s = reinterpret_cast<const float*>(a.src) + ((size_t)n * 3 * a.H + h) * a.W + w;
-                const size_t cs = (size_t)a.H * a.W;
-                val.x = pack_bf16x2(__ldg(s), __ldg(s + cs));
-                val.y = pack_bf16x2(__ldg(s + 2 * cs), c3);
-            } else {
-                val.y = pack_bf16x2(0.f, c3);
-            }
-            *reinterpret_cast<uint4*>(dst) = val;
         } else {  // CVAE_LOAD_S2D_NCHW3_DTANH: 12 channels (a,b,c) + 4 zeros, two planes
             float f[16];
 #pragma unroll
@@ -147,13 +174,23 @@ __device__ __forceinline__ void fill_planes(const PlaneSrc& a, uint8_t* planes, 
                 const int H2 = 2 * a.H, W2 = 2 * a.W;
                 const float* g = reinterpret_cast<const float*>(a.src);
                 const float* rc = reinterpret_cast<const float*>(a.src2);
+                // the two horizontal phases of a row are adjacent floats (2w is even): one 8-byte load each
+                float2 gv[6], rv[6];
 #pragma unroll
-                for (int ab = 0; ab < 4; ++ab)
+                for (int a2 = 0; a2 < 2; ++a2)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const size_t idx = (((size_t)n * 3 + c) * H2 + 2 * h + (ab >> 1)) * W2 + 2 * w + (ab & 1);
-                        const float rv = __ldg(rc + idx);
-                        f[ab * 3 + c] = __ldg(g + idx) * (1.f - rv * rv);
+                        const size_t idx = (((size_t)n * 3 + c) * H2 + 2 * h + a2) * W2 + 2 * w;
+                        gv[a2 * 3 + c] = __ldg(reinterpret_cast<const float2*>(g + idx));
+                        rv[a2 * 3 + c] = __ldg(reinterpret_cast<const float2*>(rc + idx));
+                    }
+#pragma unroll
+                for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float2 gg = gv[a2 * 3 + c], rr = rv[a2 * 3 + c];
+                        f[(a2 * 2 + 0) * 3 + c] = gg.x * (1.f - rr.x * rr.x);
+                        f[(a2 * 2 + 1) * 3 + c] = gg.y * (1.f - rr.y * rr.y);
                     }
             }
             uint4 p0, p1;
