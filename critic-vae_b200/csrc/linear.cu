@@ -22,6 +22,30 @@ namespace cvae {
 // order and adds the bias -- one launch, no atomics, bit-reproducible.
 static constexpr int kFcRows = 16, kFcSplit = 8, kFcSlice = 4096 / kFcSplit;
 static constexpr size_t kFcSmem = (size_t)kFcSlice * 64 * 4 + (size_t)kFcRows * kFcSlice * 2;
+// [16 rows][64] partial of one K slice: thread -> output j = tid % 64, rows 4 (tid / 64) .. + 3 (a warp shares the rows: the
+// activation reads are broadcasts).  Shared by fc_fwd_kernel and bottleneck_fwd_kernel (bit-identical results).
+__device__ __forceinline__ void fc_slice_partial(const uint32_t* __restrict__ sa, const float* __restrict__ sw, float (*part)[64]) {
+    const int j = threadIdx.x & 63, rq = threadIdx.x >> 6;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int k8 = 0; k8 < kFcSlice / 8; ++k8) {
+        uint4 xr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xr[i] = *reinterpret_cast<const uint4*>(sa + (rq * 4 + i) * (kFcSlice / 2) + k8 * 4);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const float wv = sw[(k8 * 8 + kk) * 64 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t u = (kk >> 1) == 0 ? xr[i].x : ((kk >> 1) == 1 ? xr[i].y : ((kk >> 1) == 2 ? xr[i].z : xr[i].w));
+                acc[i] = fmaf(wv, (kk & 1) ? bf16_hi(u) : bf16_lo(u), acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) part[rq * 4 + i][j] = acc[i];
+}
+
 __global__ void __cluster_dims__(kFcSplit, 1, 1) __launch_bounds__(256)
 fc_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restrict__ wfc,
               const float* __restrict__ bmu, const float* __restrict__ bvar, float* __restrict__ ml, int* fault) {
@@ -49,25 +73,7 @@ fc_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restric
         __syncwarp();
     }
     mbar_wait(&bar, 0, fault);
-    const int j = threadIdx.x & 63, rq = threadIdx.x >> 6;   // a warp shares rq: the activation reads are broadcasts
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-    for (int k8 = 0; k8 < kFcSlice / 8; ++k8) {
-        uint4 xr[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xr[i] = *reinterpret_cast<const uint4*>(sa + (rq * 4 + i) * (kFcSlice / 2) + k8 * 4);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            const float wv = sw[(k8 * 8 + kk) * 64 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t u = (kk >> 1) == 0 ? xr[i].x : ((kk >> 1) == 1 ? xr[i].y : ((kk >> 1) == 2 ? xr[i].z : xr[i].w));
-                acc[i] = fmaf(wv, (kk & 1) ? bf16_hi(u) : bf16_lo(u), acc[i]);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) part[rq * 4 + i][j] = acc[i];
+    fc_slice_partial(sa, sw, part);
     cluster.sync();
     if (threadIdx.x < 128) {
         const int r = rank * 2 + (threadIdx.x >> 6), jj = threadIdx.x & 63;
@@ -77,6 +83,17 @@ fc_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restric
         if (b0 + r < B) ml[(size_t)(b0 + r) * 64 + jj] = s + (jj < 32 ? bmu[jj] : bvar[jj - 32]);
     }
     cluster.sync();   // nobody leaves while a peer may still read its partial
+}
+
+// fc backward (data) for ONE output k' and 8 rows: the expression fc_bwd_data_kernel uses, shared with the fused kernel
+__device__ __forceinline__ void fc_bwd_row8(const float4* __restrict__ wr, const float (*sd)[64], float* acc) {
+#pragma unroll 4
+    for (int q = 0; q < 16; ++q) {
+        const float4 w = __ldg(wr + q);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            acc[r] += w.x * sd[r][4 * q] + w.y * sd[r][4 * q + 1] + w.z * sd[r][4 * q + 2] + w.w * sd[r][4 * q + 3];
+    }
 }
 
 // ---- fc backward (data): da[b][k'] = sum_j dml[b][j] * wfc[k'][j]  (gradient w.r.t. the Tanh output) ----
@@ -94,14 +111,7 @@ __global__ void fc_bwd_data_kernel(int B, const float* __restrict__ dml, const f
         float acc[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-        const float4* wr = reinterpret_cast<const float4*>(wfc + (size_t)k * 64);
-#pragma unroll 4
-        for (int q = 0; q < 16; ++q) {
-            const float4 w = __ldg(wr + q);
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                acc[r] += w.x * sd[r][4 * q] + w.y * sd[r][4 * q + 1] + w.z * sd[r][4 * q + 2] + w.w * sd[r][4 * q + 3];
-        }
+        fc_bwd_row8(reinterpret_cast<const float4*>(wfc + (size_t)k * 64), sd, acc);
 #pragma unroll
         for (int r = 0; r < 8; ++r)
             if (b0 + r < B) da[(size_t)(b0 + r) * 4096 + k] = __float2bfloat16_rn(acc[r]);
@@ -192,6 +202,33 @@ __global__ void decin_fwd_kernel(int B, const float* __restrict__ zc, const floa
 // arrive by bulk async copies, partial [16][33] tiles are combined over distributed shared memory in rank order.
 static constexpr int kDdRows = 16, kDdSplit = 8, kDdSlice = 4096 / kDdSplit, kDdWStride = kDdSlice + 4;  // floats; +4 keeps rows 16 B aligned
 static constexpr size_t kDdSmem = (size_t)33 * kDdWStride * 4 + (size_t)kDdRows * kDdSlice * 2;
+// [16 rows][33] partial of one K slice: thread -> row r = tid / 16, outputs i = ig, ig + 16 (and 32 for ig == 0).
+// Shared by decin_bwd_data_kernel and bottleneck_bwd_kernel (bit-identical results).
+__device__ __forceinline__ void decin_slice_partial(const uint32_t* __restrict__ sd, const float* __restrict__ sw, float (*part)[33]) {
+    const int r = threadIdx.x >> 4, ig = threadIdx.x & 15;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    const float* w0 = sw + ig * kDdWStride;
+    const float* w1 = sw + (ig + 16) * kDdWStride;
+    const float* w2 = sw + 32 * kDdWStride;
+    const uint32_t* xr = sd + r * (kDdSlice / 2);
+#pragma unroll 4
+    for (int kp = 0; kp < kDdSlice / 2; ++kp) {
+        const uint32_t u = xr[kp];
+        const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+        const float2 a = *reinterpret_cast<const float2*>(w0 + 2 * kp);
+        const float2 b = *reinterpret_cast<const float2*>(w1 + 2 * kp);
+        acc0 = fmaf(x0, a.x, acc0); acc0 = fmaf(x1, a.y, acc0);
+        acc1 = fmaf(x0, b.x, acc1); acc1 = fmaf(x1, b.y, acc1);
+        if (ig == 0) {
+            const float2 c = *reinterpret_cast<const float2*>(w2 + 2 * kp);
+            acc2 = fmaf(x0, c.x, acc2); acc2 = fmaf(x1, c.y, acc2);
+        }
+    }
+    part[r][ig] = acc0;
+    part[r][ig + 16] = acc1;
+    if (ig == 0) part[r][32] = acc2;
+}
+
 __global__ void __cluster_dims__(kDdSplit, 1, 1) __launch_bounds__(256)
 decin_bwd_data_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* __restrict__ wdec, float* __restrict__ dzc, int* fault) {
     grid_dependency_sync();
@@ -216,29 +253,7 @@ decin_bwd_data_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* 
         __syncwarp();
     }
     mbar_wait(&bar, 0, fault);
-    // thread -> row r = tid / 16, outputs i = ig, ig + 16 (and 32 for ig == 0)
-    const int r = threadIdx.x >> 4, ig = threadIdx.x & 15;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-    const float* w0 = sw + ig * kDdWStride;
-    const float* w1 = sw + (ig + 16) * kDdWStride;
-    const float* w2 = sw + 32 * kDdWStride;
-    const uint32_t* xr = sd + r * (kDdSlice / 2);
-#pragma unroll 4
-    for (int kp = 0; kp < kDdSlice / 2; ++kp) {
-        const uint32_t u = xr[kp];
-        const float x0 = bf16_lo(u), x1 = bf16_hi(u);
-        const float2 a = *reinterpret_cast<const float2*>(w0 + 2 * kp);
-        const float2 b = *reinterpret_cast<const float2*>(w1 + 2 * kp);
-        acc0 = fmaf(x0, a.x, acc0); acc0 = fmaf(x1, a.y, acc0);
-        acc1 = fmaf(x0, b.x, acc1); acc1 = fmaf(x1, b.y, acc1);
-        if (ig == 0) {
-            const float2 c = *reinterpret_cast<const float2*>(w2 + 2 * kp);
-            acc2 = fmaf(x0, c.x, acc2); acc2 = fmaf(x1, c.y, acc2);
-        }
-    }
-    part[r][ig] = acc0;
-    part[r][ig + 16] = acc1;
-    if (ig == 0) part[r][32] = acc2;
+    decin_slice_partial(sd, sw, part);
     cluster.sync();
     if (threadIdx.x < 66) {
         const int rr = rank * 2 + threadIdx.x / 33, i = threadIdx.x % 33;
@@ -284,9 +299,224 @@ __global__ void __launch_bounds__(256) decin_bwd_weight_kernel(int B, const __nv
     }
 }
 
+// =============================================================================================
+// The bottleneck in one launch per direction (training path).  Both are latency chains of three small layers
+// (0.17 % of the FLOPs, ~60 us of the step's main chain as separate launches):
+//   forward :  fc_mu || fc_var  ->  reparametrise + critic concat  ->  decoder_input
+//   backward:  decoder_input^T  ->  reparametrise backward (+ KL gradient)  ->  (fc_mu || fc_var)^T
+// Same decomposition as the separate kernels: a cluster of 8 CTAs owns 16 batch rows; the K = 4096 reduction of the first
+// layer is split over the cluster and combined over distributed shared memory in rank order; CTA r finishes rows 2r, 2r+1,
+// does their latent arithmetic, publishes the 33 (64) values per row in its shared memory, and after one more cluster
+// barrier every CTA reads all 16 rows and produces ITS 512-wide slice of the last layer.  The arithmetic is shared with
+// the separate kernels (fc_slice_partial, decin_slice_partial, same expressions), so the results are bit-identical.
+// =============================================================================================
+static constexpr size_t kBnFwdSmem = kFcSmem + (size_t)34 * kFcSlice * 4;     // fc operands + this CTA's [34][512] decoder_input slice
+__global__ void __cluster_dims__(kFcSplit, 1, 1) __launch_bounds__(256)
+bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restrict__ wfc, const float* __restrict__ bmu,
+                      const float* __restrict__ bvar, const float* __restrict__ eps, const float* __restrict__ pred,
+                      const float* __restrict__ wdec, float* __restrict__ ml, float* __restrict__ zc, __nv_bfloat16* __restrict__ h,
+                      int* fault) {
+    extern __shared__ __align__(128) uint8_t bn_smem[];
+    float* sw = reinterpret_cast<float*>(bn_smem);                                        // [512][64]
+    uint32_t* sa = reinterpret_cast<uint32_t*>(bn_smem + (size_t)kFcSlice * 64 * 4);      // [16][256] bf16 pairs
+    float* swd = reinterpret_cast<float*>(bn_smem + kFcSmem);                             // [34][512]
+    __shared__ float part[kFcRows][64];
+    __shared__ float ml_own[2][64];
+    __shared__ float z_own[2][33];
+    __shared__ float z_all[kFcRows][33];
+    __shared__ uint64_t bar[2];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = (blockIdx.x / kFcSplit) * kFcRows, k0 = rank * kFcSlice;
+    const int rows = min(kFcRows, B - b0);
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    for (int i = threadIdx.x; i < (kFcRows - rows) * (kFcSlice / 2); i += 256) sa[rows * (kFcSlice / 2) + i] = 0u;
+    __syncthreads();
+    grid_dependency_sync();
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            mbar_expect_tx(&bar[0], (uint32_t)(kFcSlice * 64 * 4 + rows * kFcSlice * 2));
+            for (int c = 0; c < 8; ++c)
+                bulk_g2s(bn_smem + (size_t)c * 16384, reinterpret_cast<const uint8_t*>(wfc + (size_t)k0 * 64) + (size_t)c * 16384, 16384, &bar[0]);
+            for (int r = 0; r < rows; ++r)
+                bulk_g2s(sa + r * (kFcSlice / 2), a + (size_t)(b0 + r) * 4096 + k0, kFcSlice * 2, &bar[0]);
+            mbar_expect_tx(&bar[1], (uint32_t)(34 * kFcSlice * 4));       // needed two cluster barriers from now
+            for (int i = 0; i < 34; ++i) bulk_g2s(swd + i * kFcSlice, wdec + (size_t)i * 4096 + k0, kFcSlice * 4, &bar[1]);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&bar[0], 0, fault);
+    fc_slice_partial(sa, sw, part);
+    cluster.sync();
+    if (threadIdx.x < 128) {                     // rows 2 rank, 2 rank + 1: combine the eight K slices in rank order (as fc_fwd_kernel)
+        const int rr = threadIdx.x >> 6, r = rank * 2 + rr, jj = threadIdx.x & 63;
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < kFcSplit; ++q) s += cluster.map_shared_rank(&part[0][0], q)[r * 64 + jj];
+        s += (jj < 32 ? bmu[jj] : bvar[jj - 32]);
+        ml_own[rr][jj] = s;
+        if (b0 + r < B) ml[(size_t)(b0 + r) * 64 + jj] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 66) {                      // z = mu + eps * exp(logvar / 2) | critic value  (latent_fwd_kernel's expressions)
+        const int rr = threadIdx.x / 33, d = threadIdx.x % 33, r = rank * 2 + rr;
+        float z = 0.f;
+        if (b0 + r < B) {
+            if (d < 32) z = fmaf(__ldg(eps + (size_t)(b0 + r) * 32 + d), expf(0.5f * ml_own[rr][32 + d]), ml_own[rr][d]);
+            else z = __ldg(pred + b0 + r);
+            zc[(size_t)(b0 + r) * 33 + d] = z;
+        }
+        z_own[rr][d] = z;
+    }
+    cluster.sync();
+    for (int i = threadIdx.x; i < kFcRows * 33; i += 256) {
+        const int r = i / 33, d = i - r * 33;
+        z_all[r][d] = cluster.map_shared_rank(&z_own[0][0], r >> 1)[(r & 1) * 33 + d];
+    }
+    __syncthreads();
+    mbar_wait(&bar[1], 0, fault);
+    {   // decoder_input slice: thread -> outputs k0 + 2 tid, + 1 for all 16 rows (decin_fwd_kernel's accumulation order)
+        const int kk = 2 * threadIdx.x;
+        float acc0[kFcRows], acc1[kFcRows];
+        const float2 bias = *reinterpret_cast<const float2*>(swd + 33 * kFcSlice + kk);
+#pragma unroll
+        for (int r = 0; r < kFcRows; ++r) { acc0[r] = bias.x; acc1[r] = bias.y; }
+        for (int i = 0; i < 33; ++i) {
+            const float2 w = *reinterpret_cast<const float2*>(swd + i * kFcSlice + kk);
+#pragma unroll
+            for (int r = 0; r < kFcRows; ++r) {
+                const float z = z_all[r][i];
+                acc0[r] = fmaf(w.x, z, acc0[r]);
+                acc1[r] = fmaf(w.y, z, acc1[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kFcRows; ++r)
+            if (b0 + r < B) *reinterpret_cast<uint32_t*>(h + (size_t)(b0 + r) * 4096 + k0 + kk) = pack_bf16x2(acc0[r], acc1[r]);
+    }
+    cluster.sync();   // nobody leaves while a peer may still read its partials / latent rows
+}
+
+static constexpr size_t kBnBwdSmem = kDdSmem;
+__global__ void __cluster_dims__(kDdSplit, 1, 1) __launch_bounds__(256)
+bottleneck_bwd_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* __restrict__ wdec, const float* __restrict__ ml,
+                      const float* __restrict__ eps, float kld_grad_scale, const float* __restrict__ wfc, float* __restrict__ dzc,
+                      float* __restrict__ dml, __nv_bfloat16* __restrict__ da, int* fault) {
+    extern __shared__ __align__(128) uint8_t bb_smem[];
+    float* sw = reinterpret_cast<float*>(bb_smem);                                            // [33][516]
+    uint32_t* sd = reinterpret_cast<uint32_t*>(bb_smem + (size_t)33 * kDdWStride * 4);         // [16][256] bf16 pairs
+    __shared__ float part[kDdRows][33];
+    __shared__ float dz_own[2][33];
+    __shared__ float dml_own[2][64];
+    __shared__ float dml_all[kDdRows][64];
+    __shared__ uint64_t bar;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = (blockIdx.x / kDdSplit) * kDdRows, k0 = rank * kDdSlice;
+    const int rows = min(kDdRows, B - b0);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (int i = threadIdx.x; i < (kDdRows - rows) * (kDdSlice / 2); i += 256) sd[rows * (kDdSlice / 2) + i] = 0u;
+    __syncthreads();
+    grid_dependency_sync();
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            mbar_expect_tx(&bar, (uint32_t)(33 * kDdSlice * 4 + rows * kDdSlice * 2));
+            for (int i = 0; i < 33; ++i) bulk_g2s(sw + i * kDdWStride, wdec + (size_t)i * 4096 + k0, kDdSlice * 4, &bar);
+            for (int r = 0; r < rows; ++r) bulk_g2s(sd + r * (kDdSlice / 2), dh + (size_t)(b0 + r) * 4096 + k0, kDdSlice * 2, &bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&bar, 0, fault);
+    decin_slice_partial(sd, sw, part);
+    cluster.sync();
+    if (threadIdx.x < 66) {                      // rows 2 rank, 2 rank + 1 (as decin_bwd_data_kernel)
+        const int rr = threadIdx.x / 33, r = rank * 2 + rr, i = threadIdx.x % 33;
+        float sacc = 0.f;
+#pragma unroll
+        for (int q = 0; q < kDdSplit; ++q) sacc += cluster.map_shared_rank(&part[0][0], q)[r * 33 + i];
+        dz_own[rr][i] = sacc;
+        if (dzc && b0 + r < B) dzc[(size_t)(b0 + r) * 33 + i] = sacc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {                      // reparametrise backward + KL gradient (latent_bwd_kernel's expressions, no external terms)
+        const int rr = threadIdx.x >> 5, d = threadIdx.x & 31, r = rank * 2 + rr;
+        float om = 0.f, ol = 0.f;
+        if (b0 + r < B) {
+            const float mu = __ldg(ml + (size_t)(b0 + r) * 64 + d), lv = __ldg(ml + (size_t)(b0 + r) * 64 + 32 + d);
+            const float e = __ldg(eps + (size_t)(b0 + r) * 32 + d), dz = dz_own[rr][d];
+            const float std_ = expf(0.5f * lv);
+            om = dz + 0.f;
+            ol = dz * e * 0.5f * std_ + 0.f;
+            if (kld_grad_scale != 0.f) {
+                om += kld_grad_scale * mu;
+                ol += kld_grad_scale * 0.5f * (expf(lv) - 1.f);
+            }
+            dml[(size_t)(b0 + r) * 64 + d] = om;
+            dml[(size_t)(b0 + r) * 64 + 32 + d] = ol;
+        }
+        dml_own[rr][d] = om;
+        dml_own[rr][32 + d] = ol;
+    }
+    cluster.sync();
+    for (int i = threadIdx.x; i < kDdRows * 64; i += 256) {
+        const int r = i >> 6, j = i & 63;
+        dml_all[r][j] = cluster.map_shared_rank(&dml_own[0][0], r >> 1)[(r & 1) * 64 + j];
+    }
+    __syncthreads();
+    {   // (fc_mu || fc_var)^T slice: thread -> k' = k0 + 2 tid, + 1, 16 rows as two groups of 8 (fc_bwd_data_kernel's expression)
+        const int kp = k0 + 2 * threadIdx.x;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float acc0[8], acc1[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc0[r] = acc1[r] = 0.f;
+            fc_bwd_row8(reinterpret_cast<const float4*>(wfc + (size_t)kp * 64), dml_all + half * 8, acc0);
+            fc_bwd_row8(reinterpret_cast<const float4*>(wfc + (size_t)(kp + 1) * 64), dml_all + half * 8, acc1);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (b0 + half * 8 + r < B)
+                    *reinterpret_cast<uint32_t*>(da + (size_t)(b0 + half * 8 + r) * 4096 + kp) = pack_bf16x2(acc0[r], acc1[r]);
+        }
+    }
+    cluster.sync();
+}
+
 }  // namespace cvae
 
 using namespace cvae;
+
+// vae_nets.py:108-111 + :48-51 + :143-144 in one launch (training path: z is sampled with the caller's eps).
+// Outputs: mu_logvar fp32 [B][64], z_pred fp32 [B][33], dec_in bf16 [B][4096] (NHWC 4x4x256).
+extern "C" int cvae_bottleneck_fwd(int batch, const void* act, const float* wfc, const float* bias_mu, const float* bias_var,
+                                   const float* eps, const float* pred, const float* wdec, float* mu_logvar, float* z_pred,
+                                   void* dec_in, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVAE_REQUIRE(batch > 0 && act && wfc && bias_mu && bias_var && eps && pred && wdec && mu_logvar && z_pred && dec_in, CVAE_EINVAL,
+                 "bottleneck_fwd: bad argument");
+    CVAE_OPT_IN_SMEM(bottleneck_fwd_kernel, kBnFwdSmem);
+    int* fault = fault_flag();
+    CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "bottleneck_fwd: fault flag unavailable");
+    cvae::launch(bottleneck_fwd_kernel, ((batch + kFcRows - 1) / kFcRows) * kFcSplit, 256, kBnFwdSmem, stream, batch, (const __nv_bfloat16*)act, wfc,
+                 bias_mu, bias_var, eps, pred, wdec, mu_logvar, z_pred, (__nv_bfloat16*)dec_in, fault);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+// The data-gradient chain of the same three layers in one launch: d_dec_in bf16 [B][4096] -> d_z_pred fp32 [B][33] (optional),
+// d_mu_logvar fp32 [B][64] (with the KL gradient kld_grad_scale * (mu | (exp(logvar) - 1) / 2) folded in), d_act bf16 [B][4096].
+extern "C" int cvae_bottleneck_bwd(int batch, const void* d_dec_in, const float* wdec, const float* mu_logvar, const float* eps,
+                                   float kld_grad_scale, const float* wfc, float* d_z_pred, float* d_mu_logvar, void* d_act,
+                                   void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVAE_REQUIRE(batch > 0 && d_dec_in && wdec && mu_logvar && eps && wfc && d_mu_logvar && d_act, CVAE_EINVAL, "bottleneck_bwd: bad argument");
+    CVAE_OPT_IN_SMEM(bottleneck_bwd_kernel, kBnBwdSmem);
+    int* fault = fault_flag();
+    CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "bottleneck_bwd: fault flag unavailable");
+    cvae::launch(bottleneck_bwd_kernel, ((batch + kDdRows - 1) / kDdRows) * kDdSplit, 256, kBnBwdSmem, stream, batch, (const __nv_bfloat16*)d_dec_in,
+                 wdec, mu_logvar, eps, kld_grad_scale, wfc, d_z_pred, d_mu_logvar, (__nv_bfloat16*)d_act, fault);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
 
 extern "C" int cvae_fc_fwd(int batch, const void* act, const float* wfc, const float* bias_mu,
                            const float* bias_var, float* mu_logvar, void* stream_) {

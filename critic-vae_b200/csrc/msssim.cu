@@ -335,6 +335,16 @@ static size_t ms_smem(bool bwd) {
     return sizeof(float) * (size_t)(2 * kPyr + 5 * kPyr + (bwd ? 3 * kPyr : 0));
 }
 
+// One persistent CTA per SM walks planes blockIdx.x, + grid, ...: with 768 planes on 148 SMs the sixth round would run on 28
+// SMs only.  Launch the fewest CTAs that still need the same number of rounds (768 / 6 = 128): same duration, and the
+// other SMs stay free for the kernels of the side streams.
+static int ms_grid(int planes) {
+    const int sms = sm_count();
+    if (planes <= sms) return planes;
+    const int rounds = (planes + sms - 1) / sms;
+    return (planes + rounds - 1) / rounds;
+}
+
 extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar, const double* kld_partial,
                              const float* window11, float kld_weight, double* sums, float* coef, float* losses,
                              void* stream_) {
@@ -345,7 +355,7 @@ extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, cons
     CVAE_OPT_IN_SMEM(msssim_kernel<false>, ms_smem(false));
     CVAE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 10, stream));
     const int planes = batch * 3;
-    const int grid = planes < sm_count() ? planes : sm_count();
+    const int grid = ms_grid(planes);
     cvae::launch(msssim_kernel<false>, grid, kMsThreads, ms_smem(false), stream, planes, recon, x, w, sums, nullptr, nullptr, nullptr);
     CVAE_LAUNCH_CHECK();
     cvae::launch(loss_finalize_kernel, 1, kld_partial ? 32 : 1024, 0, stream, batch, mu_logvar, kld_partial, (batch + 63) / 64, sums, kld_weight, losses, coef);
@@ -363,7 +373,7 @@ extern "C" int cvae_loss_bwd(int batch, const float* recon, const float* x, cons
     memcpy(w.g, window11, sizeof(w.g));
     CVAE_OPT_IN_SMEM(msssim_kernel<true>, ms_smem(true));
     const int planes = batch * 3;
-    const int grid = planes < sm_count() ? planes : sm_count();
+    const int grid = ms_grid(planes);
     cvae::launch(msssim_kernel<true>, grid, kMsThreads, ms_smem(true), stream, planes, recon, x, w, nullptr, coef, grad_out, d_recon);
     CVAE_LAUNCH_CHECK();
     if (d_mu) {   // NULL, NULL: the caller folds the KL term's backward into cvae_latent_bwd (kld_grad_scale)

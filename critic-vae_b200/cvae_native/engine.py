@@ -138,6 +138,8 @@ class VAEEngine:
         self.side_stream = None
         self.fold_stream = None     # third stream: split-K folds beside the next weight-gradient GEMM
         self.early_event = None     # optional torch.cuda.Event(external=True) recorded when the early gradient bucket is final
+        # the three layers around the latent as one launch per direction in the training step (CVAE_NO_FUSED_BOTTLENECK=1: six launches)
+        self.fused_bottleneck = os.environ.get("CVAE_NO_FUSED_BOTTLENECK") is None
 
     # ---- parameters ---------------------------------------------------------------------------
     def view(self, name, buf=None):
@@ -273,8 +275,9 @@ class VAEEngine:
         self._timed("conv_gemm", lambda: L.check(L.lib.cvae_conv_gemm(ctypes.byref(d), L.stream_ptr())))
 
     @_nvtx("encode")
-    def encode(self, x, training, ws, pack=True):
-        """x fp32 NCHW [B,3,64,64] -> ws.ml = mu | logvar.  vae_nets.py:101-111."""
+    def encode(self, x, training, ws, pack=True, fc=True):
+        """x fp32 NCHW [B,3,64,64] -> ws.ml = mu | logvar.  vae_nets.py:101-111.
+        fc=False stops in front of fc_mu / fc_var (the training step runs them inside bottleneck_forward)."""
         B, s = ws.B, L.stream_ptr()
         if pack:
             self.pack()
@@ -299,21 +302,33 @@ class VAEEngine:
                                       _ptr(self.view(bname + ".weight")), _ptr(self.view(bname + ".bias")), _ptr(self.view(cname + ".bias")),
                                       _ptr(self.running_mean[i]), _ptr(self.running_var[i]), _ptr(self.nbt[i]), BN_MOMENTUM, BN_EPS,
                                       _ptr(ws.ss[i]), _ptr(ws.a[i]), _ptr(ws.xh[i]) if save else None, _ptr(ws.am[i]) if save else None, s))
-        L.check(L.lib.cvae_fc_fwd(B, _ptr(ws.a[3]), _ptr(self.packed["fc"]), _ptr(self.view("encoder.fc_mu.bias")),
-                                  _ptr(self.view("encoder.fc_var.bias")), _ptr(ws.ml), s))
+        if fc:
+            L.check(L.lib.cvae_fc_fwd(B, _ptr(ws.a[3]), _ptr(self.packed["fc"]), _ptr(self.view("encoder.fc_mu.bias")),
+                                      _ptr(self.view("encoder.fc_var.bias")), _ptr(ws.ml), s))
         return ws.ml
 
+    @_nvtx("bottleneck_forward")
+    def bottleneck_forward(self, pred, eps, ws):
+        """fc_mu || fc_var -> reparametrise + critic concat -> decoder_input in one launch (vae_nets.py:108-111, 48-51,
+        143-144): ws.a[3] -> ws.ml, ws.zc, ws.h0.  Training path (z is sampled); bit-identical to the three kernels."""
+        self._await_fwd_pack()
+        L.check(L.lib.cvae_bottleneck_fwd(ws.B, _ptr(ws.a[3]), _ptr(self.packed["fc"]), _ptr(self.view("encoder.fc_mu.bias")),
+                                          _ptr(self.view("encoder.fc_var.bias")), _ptr(eps), _ptr(pred), _ptr(self.packed["decin"]),
+                                          _ptr(ws.ml), _ptr(ws.zc), _ptr(ws.h0), L.stream_ptr()))
+
     @_nvtx("decode")
-    def decode(self, pred, eps, sample, ws, pack=False):
-        """ws.ml, pred fp32 [B] (+ eps fp32 [B,32]) -> ws.recon fp32 NCHW.  vae_nets.py:48-51,139-147."""
+    def decode(self, pred, eps, sample, ws, pack=False, head=True):
+        """ws.ml, pred fp32 [B] (+ eps fp32 [B,32]) -> ws.recon fp32 NCHW.  vae_nets.py:48-51,139-147.
+        head=False starts behind decoder_input (ws.h0 comes from bottleneck_forward)."""
         B, s = ws.B, L.stream_ptr()
         if pack:
             self.pack()
         self._await_fwd_pack()       # (a decode() that packs itself, e.g. Decoder.forward: "fc" / "decin" are forward forms)
-        # fused reparametrise + critic concat + KL partial sums (consumed by loss_forward when it is given ws.ml itself)
-        L.check(L.lib.cvae_latent_fwd(B, int(sample), _ptr(ws.ml), _ptr(eps), _ptr(pred), _ptr(ws.zc),
-                                      _ptr(ws.kld_partial) if sample else None, s))
-        L.check(L.lib.cvae_decin_fwd(B, _ptr(ws.zc), _ptr(self.packed["decin"]), _ptr(ws.h0), s))
+        if head:
+            # fused reparametrise + critic concat + KL partial sums (consumed by loss_forward when it is given ws.ml itself)
+            L.check(L.lib.cvae_latent_fwd(B, int(sample), _ptr(ws.ml), _ptr(eps), _ptr(pred), _ptr(ws.zc),
+                                          _ptr(ws.kld_partial) if sample else None, s))
+            L.check(L.lib.cvae_decin_fwd(B, _ptr(ws.zc), _ptr(self.packed["decin"]), _ptr(ws.h0), s))
         bias = lambda i: self.view(f"decoder.model.{DEC_CONV_IDX[i]}.bias")
         self._conv("D0f", batch=B, height=4, width=4, ksize=5, src_channels=256, n_total=128, loader=L.LOAD_NHWC,
                    epilogue=L.EPI_BIAS_RELU, ktab=L.KTAB_GENERIC, src=ws.h0, wpack=self.packed["D0f"], out=ws.d[0], bias=bias(0))
@@ -331,7 +346,8 @@ class VAEEngine:
     @_nvtx("loss_forward")
     def loss_forward(self, recon, x, ml, ws, kld_weight=KLD_WEIGHT, fused_kld=False):
         """`fused_kld`: ml is ws.ml of the decode() that just ran with sample=True, so the KL partial sums the latent
-        kernel left in ws.kld_partial are used instead of re-reading mu / logvar (TrainStep)."""
+        kernel left in ws.kld_partial are used instead of re-reading mu / logvar (a decode() with its head; after
+        bottleneck_forward there are no partials and the loss kernel reduces mu / logvar itself)."""
         L.check(L.lib.cvae_loss_fwd(ws.B, _ptr(recon), _ptr(x), _ptr(ml), _ptr(ws.kld_partial) if fused_kld else None, self.window,
                                     kld_weight, _ptr(ws.loss_sums), _ptr(ws.coef), _ptr(ws.losses), L.stream_ptr()))
         return ws.losses
@@ -450,6 +466,14 @@ class VAEEngine:
         self._leaf(lambda st: L.check(L.lib.cvae_decin_bwd(B, _ptr(ws.g_h0), _ptr(ws.zc), None, None,
                                                            _ptr(G("decoder.decoder_input.weight")),
                                                            _ptr(G("decoder.decoder_input.bias")), st)))
+        if d_mu is None and d_lv is None and self.fused_bottleneck:
+            # decoder_input^T -> reparametrise backward (+ KL gradient) -> (fc_mu || fc_var)^T in one launch
+            L.check(L.lib.cvae_bottleneck_bwd(B, _ptr(ws.g_h0), _ptr(self.packed["decin"]), _ptr(ws.ml), _ptr(eps), float(kld_grad_scale),
+                                              _ptr(self.packed["fc"]), None, _ptr(ws.dml), _ptr(ws.g_a[3]), s))
+            self._leaf(lambda st: L.check(L.lib.cvae_fc_bwd(B, _ptr(ws.dml), _ptr(ws.a[3]), None, None,
+                                                            _ptr(G("encoder.fc_mu.weight")), _ptr(G("encoder.fc_var.weight")),
+                                                            _ptr(G("encoder.fc_mu.bias")), _ptr(G("encoder.fc_var.bias")), st)))
+            return
         L.check(L.lib.cvae_decin_bwd(B, _ptr(ws.g_h0), None, _ptr(self.packed["decin"]), _ptr(ws.dzc), None, None, s))
         L.check(L.lib.cvae_latent_bwd(B, _ptr(ws.ml), _ptr(eps), _ptr(ws.dzc), _ptr(d_mu), _ptr(d_lv), float(kld_grad_scale),
                                       _ptr(ws.dml), s))

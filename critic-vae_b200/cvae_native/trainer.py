@@ -102,12 +102,16 @@ class TrainStep:
                                                   L.stream_ptr()))
                     joined = torch.cuda.Event()
                     joined.record()
-        eng.encode(self.x, True, ws)
+        fused = eng.fused_bottleneck
+        eng.encode(self.x, True, ws, fc=not fused)
         if joined is not None:
             torch.cuda.current_stream().wait_event(joined)
-        eng.decode(self.pred, self.eps, True, ws)
-        # the KL term rides along with the latent kernels: partial sums in the forward, its gradient in the backward
-        eng.loss_forward(ws.recon, self.x, ws.ml, ws, fused_kld=True)
+        if fused:
+            eng.bottleneck_forward(self.pred, self.eps, ws)
+        eng.decode(self.pred, self.eps, True, ws, head=not fused)
+        # the KL term rides along with the latent kernels: partial sums in the forward (separate kernels only; the loss kernel
+        # reduces mu / logvar itself behind the fused bottleneck), its gradient in the backward
+        eng.loss_forward(ws.recon, self.x, ws.ml, ws, fused_kld=not fused)
         eng.loss_backward(ws.recon, self.x, ws.ml, ws, fused_kld=True)
         eng.early_event = self.early_event if self.overlap else None      # (the engine is shared between TrainSteps)
         eng.backward(self.x, self.eps, ws, ws.d_recon, None, None, kld_grad_scale=KLD_WEIGHT / self.B, stage=stage)

@@ -211,6 +211,17 @@ int cvae_decin_fwd(int batch, const float* z_pred, const float* wdec, void* out,
 int cvae_decin_bwd(int batch, const void* d_out, const float* z_pred, const float* wdec, float* d_z_pred,
                    float* dw, float* db, void* stream);
 
+/* The three layers around the latent in ONE launch per direction (training path; vae_nets.py:108-111, :48-51, :143-144
+ * and their data gradients).  Bit-identical to cvae_fc_fwd -> cvae_latent_fwd(sample = 1) -> cvae_decin_fwd, and to
+ * cvae_decin_bwd (data) -> cvae_latent_bwd (no external mu / logvar gradients) -> cvae_fc_bwd (data).  The weight
+ * gradients of the two layers stay with cvae_decin_bwd / cvae_fc_bwd (d_z_pred may be NULL). */
+int cvae_bottleneck_fwd(int batch, const void* act, const float* wfc, const float* bias_mu, const float* bias_var,
+                        const float* eps, const float* pred, const float* wdec, float* mu_logvar, float* z_pred,
+                        void* dec_in, void* stream);
+int cvae_bottleneck_bwd(int batch, const void* d_dec_in, const float* wdec, const float* mu_logvar, const float* eps,
+                        float kld_grad_scale, const float* wfc, float* d_z_pred, float* d_mu_logvar, void* d_act,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Latent: z = mu + eps * exp(0.5 logvar) (vae_nets.py:48-51; eps supplied by the host for parity,
  * sample = 0 decodes the mean as evaluate() does, :43-44) and the critic-value concat (:143):

@@ -200,6 +200,47 @@ def test_linear_layers(B):
     close(from_nhwc(da), a_req.grad, tol=1e-2)
 
 
+@pytest.mark.parametrize("B", [1, 19, 64, 256])
+def test_bottleneck_fused_equals_the_three_separate_kernels(B):
+    """cvae_bottleneck_fwd / _bwd (one launch per direction, the training path) against fc -> latent -> decoder_input and
+    their data gradients run one by one (checked against torch above): bit for bit, including ragged row blocks."""
+    L = _native()
+    wmu, wvar, bmu, bvar = _rand((32, 4096), 20, 0.02), _rand((32, 4096), 21, 0.02), _rand((32,), 22, 0.1), _rand((32,), 23, 0.1)
+    wd, bd = _rand((4096, 33), 24, 0.2), _rand((4096,), 25, 0.1)
+    dev = [t.cuda() for t in (wmu, wvar, bmu, bvar, wd, bd)]
+    wfc, wdec = torch.zeros(4096, 64, device="cuda"), torch.zeros(34, 4096, device="cuda")
+    jobs = (L.PackJob * 2)(L.PackJob(kind=L.PACK_FC, src=ptr(dev[0]), src2=ptr(dev[1]), dst=ptr(wfc)),
+                           L.PackJob(kind=L.PACK_DECIN, src=ptr(dev[4]), src2=ptr(dev[5]), dst=ptr(wdec)))
+    L.check(L.lib.cvae_pack_weights(jobs, 2, L.stream_ptr()))
+    a_dev = nhwc_bf16(rb(torch.tanh(_rand((B, 256, 4, 4), 26, 2.0))))
+    eps_d, pred_d = _rand((B, 32), 27).cuda(), torch.rand(B, generator=torch.Generator().manual_seed(28)).cuda()
+    s = L.stream_ptr()
+    new = lambda *shape, dt=torch.float32: torch.full(shape, float("nan"), dtype=dt, device="cuda")
+    ml1, zc1, h1 = new(B, 64), new(B, 33), new(B, 4096, dt=torch.bfloat16)
+    L.check(L.lib.cvae_fc_fwd(B, ptr(a_dev), ptr(wfc), ptr(dev[2]), ptr(dev[3]), ptr(ml1), s))
+    L.check(L.lib.cvae_latent_fwd(B, 1, ptr(ml1), ptr(eps_d), ptr(pred_d), ptr(zc1), None, s))
+    L.check(L.lib.cvae_decin_fwd(B, ptr(zc1), ptr(wdec), ptr(h1), s))
+    ml2, zc2, h2 = new(B, 64), new(B, 33), new(B, 4096, dt=torch.bfloat16)
+    L.check(L.lib.cvae_bottleneck_fwd(B, ptr(a_dev), ptr(wfc), ptr(dev[2]), ptr(dev[3]), ptr(eps_d), ptr(pred_d), ptr(wdec), ptr(ml2), ptr(zc2),
+                                      ptr(h2), s))
+    sync(L)
+    assert torch.equal(ml1, ml2) and torch.equal(zc1, zc2) and torch.equal(h1, h2)
+    # backward
+    dh = nhwc_bf16(rb(_rand((B, 256, 4, 4), 29))).reshape(B, 4096)
+    k = 0.0001 / B
+    dzc1, dml1, da1 = new(B, 33), new(B, 64), new(B, 4096, dt=torch.bfloat16)
+    L.check(L.lib.cvae_decin_bwd(B, ptr(dh), None, ptr(wdec), ptr(dzc1), None, None, s))
+    L.check(L.lib.cvae_latent_bwd(B, ptr(ml1), ptr(eps_d), ptr(dzc1), None, None, k, ptr(dml1), s))
+    L.check(L.lib.cvae_fc_bwd(B, ptr(dml1), None, ptr(wfc), ptr(da1), None, None, None, None, s))
+    dzc2, dml2, da2 = new(B, 33), new(B, 64), new(B, 4096, dt=torch.bfloat16)
+    L.check(L.lib.cvae_bottleneck_bwd(B, ptr(dh), ptr(wdec), ptr(ml1), ptr(eps_d), k, ptr(wfc), ptr(dzc2), ptr(dml2), ptr(da2), s))
+    sync(L)
+    assert torch.equal(dzc1, dzc2) and torch.equal(dml1, dml2) and torch.equal(da1, da2)
+    L.check(L.lib.cvae_bottleneck_bwd(B, ptr(dh), ptr(wdec), ptr(ml1), ptr(eps_d), k, ptr(wfc), None, ptr(dml2), ptr(da2), s))   # d_z_pred is optional
+    sync(L)
+    assert torch.equal(da1, da2)
+
+
 # ------------------------------------------------------------------------------------------------
 def _window():
     return (ctypes.c_float * 11)(*[float(v) for v in O.msssim_window_1d()])
