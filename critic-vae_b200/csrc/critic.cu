@@ -16,18 +16,21 @@ static constexpr int W0 = 0, B0 = W0 + 8 * 3 * 9, W1 = B0 + 8, B1 = W1 + 8 * 8 *
 static_assert(kCriticFloats == 11873, "critic parameter count");
 
 // conv3x3(pad 1) + ReLU + MaxPool2 on a CIN x S x S map in shared memory -> COUT x S/2 x S/2.
-// One task = one pooled pixel x 8 output channels (4 conv positions x 8 channels in registers).
-template <int CIN, int COUT, int S>
+// One task = one pooled pixel x OC output channels (4 conv positions x OC channels in registers).  OC shrinks with the
+// map so that every layer has >= 128 tasks for the 512 threads: the serial FMA chain of a task, not the FMA rate, was what
+// the small layers cost (8 channels per task left 64 and 32 threads busy in layers 3 and 4).  The accumulation order of
+// each output (ci, ky, kx) does not depend on OC: results are bit-identical.
+template <int CIN, int COUT, int S, int OC>
 __device__ __forceinline__ void conv_relu_pool(const float* __restrict__ in, const float* __restrict__ w,
                                                const float* __restrict__ b, float* __restrict__ out) {
-    constexpr int P = S / 2, G = COUT / 8;
+    constexpr int P = S / 2, G = COUT / OC;
     for (int t = threadIdx.x; t < P * P * G; t += blockDim.x) {
         const int px = t % P, py = (t / P) % P, g = t / (P * P);
-        float acc[4][8];
+        float acc[4][OC];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int o = 0; o < 8; ++o) acc[q][o] = 0.f;
+            for (int o = 0; o < OC; ++o) acc[q][o] = 0.f;
         for (int ci = 0; ci < CIN; ++ci) {
             float patch[4][4];
 #pragma unroll
@@ -38,8 +41,8 @@ __device__ __forceinline__ void conv_relu_pool(const float* __restrict__ in, con
                     patch[r][c] = (y >= 0 && y < S && x >= 0 && x < S) ? in[(ci * S + y) * S + x] : 0.f;
                 }
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                const float* wk = w + ((g * 8 + o) * CIN + ci) * 9;
+            for (int o = 0; o < OC; ++o) {
+                const float* wk = w + ((g * OC + o) * CIN + ci) * 9;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -52,15 +55,16 @@ __device__ __forceinline__ void conv_relu_pool(const float* __restrict__ in, con
             }
         }
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const float bb = b[g * 8 + o];
+        for (int o = 0; o < OC; ++o) {
+            const float bb = b[g * OC + o];
             float m = fmaxf(fmaxf(acc[0][o], acc[1][o]), fmaxf(acc[2][o], acc[3][o])) + bb;
-            out[((g * 8 + o) * P + py) * P + px] = fmaxf(m, 0.f);   // relu(max(.)+b) == max(relu(.+b))
+            out[((g * OC + o) * P + py) * P + px] = fmaxf(m, 0.f);   // relu(max(.)+b) == max(relu(.+b))
         }
     }
 }
 
-__global__ void __launch_bounds__(256, 1)
+static constexpr int kCriticThreads = 512;
+__global__ void __launch_bounds__(kCriticThreads, 1)
 critic_fwd_kernel(int frames, const float* __restrict__ x, const float* __restrict__ weights, float* __restrict__ pred) {
     grid_dependency_sync();
     extern __shared__ float sm[];
@@ -78,15 +82,15 @@ critic_fwd_kernel(int frames, const float* __restrict__ x, const float* __restri
         const float4* src = reinterpret_cast<const float4*>(x + (size_t)f * 3 * 4096);
         for (int i = threadIdx.x; i < 3 * 1024; i += blockDim.x) reinterpret_cast<float4*>(in)[i] = __ldg(src + i);
         __syncthreads();
-        conv_relu_pool<3, 8, 64>(in, wsm + W0, wsm + B0, p1);
+        conv_relu_pool<3, 8, 64, 8>(in, wsm + W0, wsm + B0, p1);
         __syncthreads();
-        conv_relu_pool<8, 8, 32>(p1, wsm + W1, wsm + B1, p2);
+        conv_relu_pool<8, 8, 32, 4>(p1, wsm + W1, wsm + B1, p2);
         __syncthreads();
-        conv_relu_pool<8, 8, 16>(p2, wsm + W2, wsm + B2, p3);
+        conv_relu_pool<8, 8, 16, 2>(p2, wsm + W2, wsm + B2, p3);
         __syncthreads();
-        conv_relu_pool<8, 16, 8>(p3, wsm + W3, wsm + B3, p4);
+        conv_relu_pool<8, 16, 8, 2>(p3, wsm + W3, wsm + B3, p4);
         __syncthreads();
-        {   // conv 4x4 valid on 16 x 4 x 4 == dot over 256 values; 8 threads per output channel
+        if (threadIdx.x < 256) {   // conv 4x4 valid on 16 x 4 x 4 == dot over 256 values; 8 threads per output channel
             const int o = threadIdx.x >> 3, part = threadIdx.x & 7;
             float s = 0.f;
             for (int k = part; k < 256; k += 8) s = fmaf(wsm[W4 + o * 256 + k], p4[k], s);
@@ -119,8 +123,10 @@ extern "C" int cvae_critic_fwd(int frames, const float* x, const float* weights,
     if (frames == 0) return CVAE_OK;
     const size_t smem = sizeof(float) * (11876 + 3 * 4096 + 8 * 1024 + 8 * 256 + 8 * 64 + 256 + 64);
     CVAE_OPT_IN_SMEM(critic_fwd_kernel, smem);
-    const int grid = frames < sm_count() ? frames : sm_count();
-    cvae::launch(critic_fwd_kernel, grid, 256, smem, (cudaStream_t)stream, frames, x, weights, pred);
+    // one frame per CTA and round: the fewest CTAs that need the same number of rounds (256 frames: 128 CTAs x 2)
+    const int sms = sm_count(), rounds = (frames + sms - 1) / sms;
+    const int grid = (frames + rounds - 1) / rounds;
+    cvae::launch(critic_fwd_kernel, grid, kCriticThreads, smem, (cudaStream_t)stream, frames, x, weights, pred);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
