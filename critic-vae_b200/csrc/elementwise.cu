@@ -388,9 +388,16 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
                             float* __restrict__ v, const long long* __restrict__ step, float lr, float b1, float b2,
                             float eps, float grad_scale) {
     grid_dependency_sync();
-    const double t = (double)(step[0] + 1);
-    const float bc1 = (float)(1.0 - pow((double)b1, t));
-    const float sq_bc2 = (float)sqrt(1.0 - pow((double)b2, t));
+    // the two double-precision pow() of the bias corrections once per block, not once per thread (they made the kernel
+    // compute-bound: 20 us at 25 % of the DRAM rate, profiles/r02_full_final.md)
+    __shared__ float bias_corr[2];
+    if (threadIdx.x == 0) {
+        const double t = (double)(step[0] + 1);
+        bias_corr[0] = (float)(1.0 - pow((double)b1, t));
+        bias_corr[1] = (float)sqrt(1.0 - pow((double)b2, t));
+    }
+    __syncthreads();
+    const float bc1 = bias_corr[0], sq_bc2 = bias_corr[1];
     const float step_size = lr / bc1;
     auto update = [&](float& pi, float gi, float& mi, float& vi) {
         const float gr = gi * grad_scale;
