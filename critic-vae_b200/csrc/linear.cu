@@ -85,14 +85,21 @@ fc_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restric
     cluster.sync();   // nobody leaves while a peer may still read its partial
 }
 
-// fc backward (data) for ONE output k' and 8 rows: the expression fc_bwd_data_kernel uses, shared with the fused kernel
-__device__ __forceinline__ void fc_bwd_row8(const float4* __restrict__ wr, const float (*sd)[64], float* acc) {
+// fc backward (data) for ONE output k' and R rows.  The 64 terms are added four at a time starting at quad
+// rot = (k' / 2) % 16 and wrapping around: with the weight rows in shared memory (256-byte pitch) the 8 lanes of a quarter
+// warp then read 8 different quads = all 32 banks (no rotation: one bank group, 8-way conflict).  fc_bwd_data_kernel reads
+// its rows from global memory and uses the same order, so the two paths stay bit-identical.
+template <int R, bool kShared>
+__device__ __forceinline__ void fc_bwd_rows(const float4* __restrict__ wr, int rot, const float (*sd)[64], float* acc) {
 #pragma unroll 4
-    for (int q = 0; q < 16; ++q) {
-        const float4 w = __ldg(wr + q);
+    for (int qq = 0; qq < 16; ++qq) {
+        const int q = (qq + rot) & 15;
+        const float4 w = kShared ? wr[q] : __ldg(wr + q);
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-            acc[r] += w.x * sd[r][4 * q] + w.y * sd[r][4 * q + 1] + w.z * sd[r][4 * q + 2] + w.w * sd[r][4 * q + 3];
+        for (int r = 0; r < R; ++r) {
+            const float4 d = *reinterpret_cast<const float4*>(&sd[r][4 * q]);
+            acc[r] += w.x * d.x + w.y * d.y + w.z * d.z + w.w * d.w;
+        }
     }
 }
 
@@ -100,7 +107,7 @@ __device__ __forceinline__ void fc_bwd_row8(const float4* __restrict__ wr, const
 __global__ void fc_bwd_data_kernel(int B, const float* __restrict__ dml, const float* __restrict__ wfc,
                                    __nv_bfloat16* __restrict__ da) {
     grid_dependency_sync();
-    __shared__ float sd[8][64];
+    __shared__ __align__(16) float sd[8][64];
     const int b0 = blockIdx.x * 8;
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
         const int r = i >> 6, jj = i & 63;
@@ -111,7 +118,7 @@ __global__ void fc_bwd_data_kernel(int B, const float* __restrict__ dml, const f
         float acc[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-        fc_bwd_row8(reinterpret_cast<const float4*>(wfc + (size_t)k * 64), sd, acc);
+        fc_bwd_rows<8, false>(reinterpret_cast<const float4*>(wfc + (size_t)k * 64), (k >> 1) & 15, sd, acc);
 #pragma unroll
         for (int r = 0; r < 8; ++r)
             if (b0 + r < B) da[(size_t)(b0 + r) * 4096 + k] = __float2bfloat16_rn(acc[r]);
@@ -211,17 +218,19 @@ __device__ __forceinline__ void decin_slice_partial(const uint32_t* __restrict__
     const float* w1 = sw + (ig + 16) * kDdWStride;
     const float* w2 = sw + 32 * kDdWStride;
     const uint32_t* xr = sd + r * (kDdSlice / 2);
-#pragma unroll 4
-    for (int kp = 0; kp < kDdSlice / 2; ++kp) {
-        const uint32_t u = xr[kp];
-        const float x0 = bf16_lo(u), x1 = bf16_hi(u);
-        const float2 a = *reinterpret_cast<const float2*>(w0 + 2 * kp);
-        const float2 b = *reinterpret_cast<const float2*>(w1 + 2 * kp);
-        acc0 = fmaf(x0, a.x, acc0); acc0 = fmaf(x1, a.y, acc0);
-        acc1 = fmaf(x0, b.x, acc1); acc1 = fmaf(x1, b.y, acc1);
+    // four k per step: 16-byte weight loads (row stride 516 floats = 4 banks: the 8 lanes of a quarter warp cover all 32
+    // banks; 8-byte loads were 2-way conflicted), same order of additions as before
+#pragma unroll 2
+    for (int k4 = 0; k4 < kDdSlice / 4; ++k4) {
+        const uint2 u = *reinterpret_cast<const uint2*>(xr + 2 * k4);
+        const float x0 = bf16_lo(u.x), x1 = bf16_hi(u.x), x2 = bf16_lo(u.y), x3 = bf16_hi(u.y);
+        const float4 a = *reinterpret_cast<const float4*>(w0 + 4 * k4);
+        const float4 b = *reinterpret_cast<const float4*>(w1 + 4 * k4);
+        acc0 = fmaf(x0, a.x, acc0); acc0 = fmaf(x1, a.y, acc0); acc0 = fmaf(x2, a.z, acc0); acc0 = fmaf(x3, a.w, acc0);
+        acc1 = fmaf(x0, b.x, acc1); acc1 = fmaf(x1, b.y, acc1); acc1 = fmaf(x2, b.z, acc1); acc1 = fmaf(x3, b.w, acc1);
         if (ig == 0) {
-            const float2 c = *reinterpret_cast<const float2*>(w2 + 2 * kp);
-            acc2 = fmaf(x0, c.x, acc2); acc2 = fmaf(x1, c.y, acc2);
+            const float4 c = *reinterpret_cast<const float4*>(w2 + 4 * k4);
+            acc2 = fmaf(x0, c.x, acc2); acc2 = fmaf(x1, c.y, acc2); acc2 = fmaf(x2, c.z, acc2); acc2 = fmaf(x3, c.w, acc2);
         }
     }
     part[r][ig] = acc0;
@@ -310,12 +319,29 @@ __global__ void __launch_bounds__(256) decin_bwd_weight_kernel(int B, const __nv
 // barrier every CTA reads all 16 rows and produces ITS 512-wide slice of the last layer.  The arithmetic is shared with
 // the separate kernels (fc_slice_partial, decin_slice_partial, same expressions), so the results are bit-identical.
 // =============================================================================================
+// profiling aid (cvae_bottleneck_debug): CTA 0 writes clock64() at its phase boundaries, 8 slots per kernel (fwd 0.., bwd 8..)
+__device__ long long* g_bn_dbg = nullptr;
+#define BN_STAMP(slot)                                                                        \
+    do {                                                                                      \
+        if (g_bn_dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g_bn_dbg[slot] = clock64(); \
+    } while (0)
+
+// every CTA: %globaltimer at entry and exit, slots 16 + 4 * blockIdx.x + {0, 1} (forward) / {2, 3} (backward)
+__device__ __forceinline__ void bn_wall(int which) {
+    if (g_bn_dbg != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_bn_dbg[16 + 4 * blockIdx.x + which] = (long long)t;
+    }
+}
+
 static constexpr size_t kBnFwdSmem = kFcSmem + (size_t)34 * kFcSlice * 4;     // fc operands + this CTA's [34][512] decoder_input slice
 __global__ void __cluster_dims__(kFcSplit, 1, 1) __launch_bounds__(256)
 bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restrict__ wfc, const float* __restrict__ bmu,
                       const float* __restrict__ bvar, const float* __restrict__ eps, const float* __restrict__ pred,
                       const float* __restrict__ wdec, float* __restrict__ ml, float* __restrict__ zc, __nv_bfloat16* __restrict__ h,
                       int* fault) {
+    bn_wall(0);
     extern __shared__ __align__(128) uint8_t bn_smem[];
     float* sw = reinterpret_cast<float*>(bn_smem);                                        // [512][64]
     uint32_t* sa = reinterpret_cast<uint32_t*>(bn_smem + (size_t)kFcSlice * 64 * 4);      // [16][256] bf16 pairs
@@ -333,6 +359,7 @@ bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* _
     for (int i = threadIdx.x; i < (kFcRows - rows) * (kFcSlice / 2); i += 256) sa[rows * (kFcSlice / 2) + i] = 0u;
     __syncthreads();
     grid_dependency_sync();
+    BN_STAMP(0);
     if (threadIdx.x < 32) {
         if (elect_one()) {
             mbar_expect_tx(&bar[0], (uint32_t)(kFcSlice * 64 * 4 + rows * kFcSlice * 2));
@@ -346,8 +373,11 @@ bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* _
         __syncwarp();
     }
     mbar_wait(&bar[0], 0, fault);
+    BN_STAMP(1);
     fc_slice_partial(sa, sw, part);
+    BN_STAMP(2);
     cluster.sync();
+    BN_STAMP(3);
     if (threadIdx.x < 128) {                     // rows 2 rank, 2 rank + 1: combine the eight K slices in rank order (as fc_fwd_kernel)
         const int rr = threadIdx.x >> 6, r = rank * 2 + rr, jj = threadIdx.x & 63;
         float s = 0.f;
@@ -374,7 +404,9 @@ bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* _
         z_all[r][d] = cluster.map_shared_rank(&z_own[0][0], r >> 1)[(r & 1) * 33 + d];
     }
     __syncthreads();
+    BN_STAMP(4);
     mbar_wait(&bar[1], 0, fault);
+    BN_STAMP(5);
     {   // decoder_input slice: thread -> outputs k0 + 2 tid, + 1 for all 16 rows (decin_fwd_kernel's accumulation order)
         const int kk = 2 * threadIdx.x;
         float acc0[kFcRows], acc1[kFcRows];
@@ -394,41 +426,54 @@ bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* _
         for (int r = 0; r < kFcRows; ++r)
             if (b0 + r < B) *reinterpret_cast<uint32_t*>(h + (size_t)(b0 + r) * 4096 + k0 + kk) = pack_bf16x2(acc0[r], acc1[r]);
     }
+    BN_STAMP(6);
     cluster.sync();   // nobody leaves while a peer may still read its partials / latent rows
+    BN_STAMP(7);
+    bn_wall(1);
 }
 
-static constexpr size_t kBnBwdSmem = kDdSmem;
+static constexpr size_t kBnBwdSmem = kDdSmem + (size_t)kDdSlice * 64 * 4;      // decoder_input operands + this CTA's [512][64] fc slice
 __global__ void __cluster_dims__(kDdSplit, 1, 1) __launch_bounds__(256)
 bottleneck_bwd_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* __restrict__ wdec, const float* __restrict__ ml,
                       const float* __restrict__ eps, float kld_grad_scale, const float* __restrict__ wfc, float* __restrict__ dzc,
                       float* __restrict__ dml, __nv_bfloat16* __restrict__ da, int* fault) {
+    bn_wall(2);
     extern __shared__ __align__(128) uint8_t bb_smem[];
     float* sw = reinterpret_cast<float*>(bb_smem);                                            // [33][516]
     uint32_t* sd = reinterpret_cast<uint32_t*>(bb_smem + (size_t)33 * kDdWStride * 4);         // [16][256] bf16 pairs
+    float* swf = reinterpret_cast<float*>(bb_smem + kDdSmem);                                  // [512][64] rows k0 .. of wfc
     __shared__ float part[kDdRows][33];
     __shared__ float dz_own[2][33];
     __shared__ float dml_own[2][64];
-    __shared__ float dml_all[kDdRows][64];
-    __shared__ uint64_t bar;
+    __shared__ __align__(16) float dml_all[kDdRows][64];
+    __shared__ uint64_t bar, bar_w;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int b0 = (blockIdx.x / kDdSplit) * kDdRows, k0 = rank * kDdSlice;
     const int rows = min(kDdRows, B - b0);
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar_w, 1); mbar_fence_init(); }
     for (int i = threadIdx.x; i < (kDdRows - rows) * (kDdSlice / 2); i += 256) sd[rows * (kDdSlice / 2) + i] = 0u;
     __syncthreads();
     grid_dependency_sync();
+    BN_STAMP(8);
     if (threadIdx.x < 32) {
         if (elect_one()) {
             mbar_expect_tx(&bar, (uint32_t)(33 * kDdSlice * 4 + rows * kDdSlice * 2));
             for (int i = 0; i < 33; ++i) bulk_g2s(sw + i * kDdWStride, wdec + (size_t)i * 4096 + k0, kDdSlice * 4, &bar);
             for (int r = 0; r < rows; ++r) bulk_g2s(sd + r * (kDdSlice / 2), dh + (size_t)(b0 + r) * 4096 + k0, kDdSlice * 2, &bar);
+            mbar_expect_tx(&bar_w, (uint32_t)(kDdSlice * 64 * 4));       // the last phase's weights: needed two cluster barriers from now
+            for (int c = 0; c < 8; ++c)
+                bulk_g2s(reinterpret_cast<uint8_t*>(swf) + (size_t)c * 16384, reinterpret_cast<const uint8_t*>(wfc + (size_t)k0 * 64) + (size_t)c * 16384,
+                         16384, &bar_w);
         }
         __syncwarp();
     }
     mbar_wait(&bar, 0, fault);
+    BN_STAMP(9);
     decin_slice_partial(sd, sw, part);
+    BN_STAMP(10);
     cluster.sync();
+    BN_STAMP(11);
     if (threadIdx.x < 66) {                      // rows 2 rank, 2 rank + 1 (as decin_bwd_data_kernel)
         const int rr = threadIdx.x / 33, r = rank * 2 + rr, i = threadIdx.x % 33;
         float sacc = 0.f;
@@ -463,27 +508,34 @@ bottleneck_bwd_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* 
         dml_all[r][j] = cluster.map_shared_rank(&dml_own[0][0], r >> 1)[(r & 1) * 64 + j];
     }
     __syncthreads();
-    {   // (fc_mu || fc_var)^T slice: thread -> k' = k0 + 2 tid, + 1, 16 rows as two groups of 8 (fc_bwd_data_kernel's expression)
-        const int kp = k0 + 2 * threadIdx.x;
+    BN_STAMP(12);
+    mbar_wait(&bar_w, 0, fault);
+    {   // (fc_mu || fc_var)^T slice: thread -> k' = k0 + 2 tid, + 1, all 16 rows, weight rows from shared memory
+        const int kl = 2 * threadIdx.x, kp = k0 + kl, rot = (kp >> 1) & 15;
+        float acc0[kDdRows], acc1[kDdRows];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float acc0[8], acc1[8];
+        for (int r = 0; r < kDdRows; ++r) acc0[r] = acc1[r] = 0.f;
+        fc_bwd_rows<kDdRows, true>(reinterpret_cast<const float4*>(swf + (size_t)kl * 64), rot, dml_all, acc0);
+        fc_bwd_rows<kDdRows, true>(reinterpret_cast<const float4*>(swf + (size_t)(kl + 1) * 64), rot, dml_all, acc1);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) acc0[r] = acc1[r] = 0.f;
-            fc_bwd_row8(reinterpret_cast<const float4*>(wfc + (size_t)kp * 64), dml_all + half * 8, acc0);
-            fc_bwd_row8(reinterpret_cast<const float4*>(wfc + (size_t)(kp + 1) * 64), dml_all + half * 8, acc1);
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (b0 + half * 8 + r < B)
-                    *reinterpret_cast<uint32_t*>(da + (size_t)(b0 + half * 8 + r) * 4096 + kp) = pack_bf16x2(acc0[r], acc1[r]);
-        }
+        for (int r = 0; r < kDdRows; ++r)
+            if (b0 + r < B) *reinterpret_cast<uint32_t*>(da + (size_t)(b0 + r) * 4096 + kp) = pack_bf16x2(acc0[r], acc1[r]);
     }
+    BN_STAMP(13);
     cluster.sync();
+    BN_STAMP(14);
+    bn_wall(3);
 }
 
 }  // namespace cvae
 
 using namespace cvae;
+
+extern "C" int cvae_bottleneck_debug(void* device_buf16) {
+    long long* p = (long long*)device_buf16;
+    CVAE_CUDA(cudaMemcpyToSymbol(g_bn_dbg, &p, sizeof(p)));
+    return CVAE_OK;
+}
 
 // vae_nets.py:108-111 + :48-51 + :143-144 in one launch (training path: z is sampled with the caller's eps).
 // Outputs: mu_logvar fp32 [B][64], z_pred fp32 [B][33], dec_in bf16 [B][4096] (NHWC 4x4x256).

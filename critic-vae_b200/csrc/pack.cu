@@ -111,43 +111,6 @@ __device__ __forceinline__ float pack_value(const cvae_pack_job& j, long long i0
     return 0.f;
 }
 
-// Which 8-element item a thread packs.  The destination order puts the K step (tap-major) far above the GEMM row, so
-// neighbouring threads would read source words 100 B (one [5][5] filter) or more apart and a whole step's worth of sectors
-// apart for the next tap: every 32-byte sector fetched for 4 useful bytes (the kernel sat at ~190 MB of L2 -> SM traffic
-// for 10 MB of weights).  Enumerate the items of a job instead as (row block of 8, channel step, TAP, row, half-step):
-// 16 consecutive threads share one tap, the next 16 take the next tap of the SAME filters, so a warp's loads fall into
-// shared sectors and a block's into a few KB that stay in L1.  A bijection on the items of the job; the values do not
-// change (tests/test_conv_gemm.py compares every form against tests/packref.py).
-__device__ __forceinline__ long long pack_locality_order(const cvae_pack_job& j, long long i0) {
-    const int base = j.kind & 0xFF;
-    if (j.kind == CVAE_PACK_FC || j.kind == CVAE_PACK_DECIN || base == CVAE_PACK_PAIR8) return i0;
-    const int NB = j.n < 128 ? j.n : 128, ngs = NB / 8;
-    int T, outer_n, spu = 1;
-    const bool block = (j.kind & (CVAE_PACK_KORDER_BLOCK64 | CVAE_PACK_KORDER_BLOCK32)) != 0;
-    if (block) {
-        const int J = (j.kind & CVAE_PACK_STACK4) ? 4 : ((j.kind & CVAE_PACK_STACK2) ? 2 : 1);
-        const int ksize = (base == CVAE_PACK_FWD5 || base == CVAE_PACK_DGRAD5) ? 5 : 3;
-        spu = ((j.kind & CVAE_PACK_KORDER_BLOCK64) ? 64 : 32) / 16;
-        T = wa_group_count(ksize, J);
-        outer_n = j.ksteps / T;                 // (channel block, 16-channel step)
-    } else {
-        outer_n = j.k_channels / 16;            // K steps per tap
-        T = j.ksteps / outer_n;                 // taps
-    }
-    if (T * outer_n != j.ksteps) return i0;     // (never for the forms the engine packs)
-    long long t = i0 >> 3;
-    const int low = (int)(t & 15);
-    t >>= 4;
-    const int tap = (int)(t % T);
-    t /= T;
-    const int outer = (int)(t % outer_n);
-    t /= outer_n;
-    const int ng = (int)(t % ngs);
-    const long long nb = t / ngs;
-    const int ks = block ? (outer / spu) * T * spu + tap * spu + (outer % spu) : tap * outer_n + outer;
-    return ((((nb * j.ksteps + ks) * ngs + ng) << 4) + low) << 3;
-}
-
 __global__ void pack_weights_kernel(const PackJobs jobs) {
     grid_dependency_sync();
     // one thread = 8 consecutive elements (every job's element count is a multiple of 8): one index decode, one 16-byte store
@@ -160,7 +123,7 @@ __global__ void pack_weights_kernel(const PackJobs jobs) {
             if (jobs.start[mid] <= idx) lo = mid; else hi = mid - 1;
         }
         const cvae_pack_job& j = jobs.job[lo];
-        const long long i0 = pack_locality_order(j, idx - jobs.start[lo]);
+        const long long i0 = idx - jobs.start[lo];
         bool is_bf16 = true;
         float v[8];
 #pragma unroll

@@ -90,6 +90,7 @@ _SIGS = {
     "cvae_loss_bwd": ([c_int, P, P, P, ctypes.POINTER(c_float), c_float, P, P, P, P, P, P], c_int),
     "cvae_adam_step": ([c_i64, P, P, P, P, P, c_float, c_float, c_float, c_float, c_float, P], c_int),
     "cvae_critic_param_count": ([], c_int),
+    "cvae_bottleneck_debug": ([P], c_int),
     "cvae_bottleneck_fwd": ([c_int] + [P] * 11, c_int),
     "cvae_bottleneck_bwd": ([c_int, P, P, P, P, ctypes.c_float, P, P, P, P, P], c_int),
     "cvae_comm_unique_id": ([P], c_int),

@@ -218,6 +218,9 @@ int cvae_decin_bwd(int batch, const void* d_out, const float* z_pred, const floa
 int cvae_bottleneck_fwd(int batch, const void* act, const float* wfc, const float* bias_mu, const float* bias_var,
                         const float* eps, const float* pred, const float* wdec, float* mu_logvar, float* z_pred,
                         void* dec_in, void* stream);
+/* profiling aid: device buffer of 16 + 4 * CTAs int64; CTA 0 of the two kernels stamps clock64() at its phase boundaries,
+ * every CTA %globaltimer at entry and exit (NULL = off) */
+int cvae_bottleneck_debug(void* device_buf16);
 int cvae_bottleneck_bwd(int batch, const void* d_dec_in, const float* wdec, const float* mu_logvar, const float* eps,
                         float kld_grad_scale, const float* wfc, float* d_z_pred, float* d_mu_logvar, void* d_act,
                         void* stream);
