@@ -24,26 +24,30 @@ static constexpr int kFcRows = 16, kFcSplit = 8, kFcSlice = 4096 / kFcSplit;
 static constexpr size_t kFcSmem = (size_t)kFcSlice * 64 * 4 + (size_t)kFcRows * kFcSlice * 2;
 // [16 rows][64] partial of one K slice: thread -> output j = tid % 64, rows 4 (tid / 64) .. + 3 (a warp shares the rows: the
 // activation reads are broadcasts).  Shared by fc_fwd_kernel and bottleneck_fwd_kernel (bit-identical results).
+template <int ROWS = 16>
 __device__ __forceinline__ void fc_slice_partial(const uint32_t* __restrict__ sa, const float* __restrict__ sw, float (*part)[64]) {
+    constexpr int RPT = ROWS / 4;     // rows per thread (ROWS = 16: the layout the stand-alone kernel has always had)
     const int j = threadIdx.x & 63, rq = threadIdx.x >> 6;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) acc[i] = 0.f;
 #pragma unroll 2
     for (int k8 = 0; k8 < kFcSlice / 8; ++k8) {
-        uint4 xr[4];
+        uint4 xr[RPT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xr[i] = *reinterpret_cast<const uint4*>(sa + (rq * 4 + i) * (kFcSlice / 2) + k8 * 4);
+        for (int i = 0; i < RPT; ++i) xr[i] = *reinterpret_cast<const uint4*>(sa + (rq * RPT + i) * (kFcSlice / 2) + k8 * 4);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             const float wv = sw[(k8 * 8 + kk) * 64 + j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPT; ++i) {
                 const uint32_t u = (kk >> 1) == 0 ? xr[i].x : ((kk >> 1) == 1 ? xr[i].y : ((kk >> 1) == 2 ? xr[i].z : xr[i].w));
                 acc[i] = fmaf(wv, (kk & 1) ? bf16_hi(u) : bf16_lo(u), acc[i]);
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) part[rq * 4 + i][j] = acc[i];
+    for (int i = 0; i < RPT; ++i) part[rq * RPT + i][j] = acc[i];
 }
 
 __global__ void __cluster_dims__(kFcSplit, 1, 1) __launch_bounds__(256)
@@ -335,7 +339,10 @@ __device__ __forceinline__ void bn_wall(int which) {
     }
 }
 
-static constexpr size_t kBnFwdSmem = kFcSmem + (size_t)34 * kFcSlice * 4;     // fc operands + this CTA's [34][512] decoder_input slice
+// ROWS batch rows per cluster: 16, or 20 when 16 would need more clusters than the device holds at once (15 eight-CTA clusters
+// at one CTA per SM: a 16th cluster -- batch 256 -- ran as a second wave and doubled the kernel's duration).
+template <int ROWS> constexpr size_t bn_fwd_smem() { return (size_t)kFcSlice * 64 * 4 + (size_t)ROWS * kFcSlice * 2 + (size_t)34 * kFcSlice * 4; }
+template <int ROWS>
 __global__ void __cluster_dims__(kFcSplit, 1, 1) __launch_bounds__(256)
 bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* __restrict__ wfc, const float* __restrict__ bmu,
                       const float* __restrict__ bvar, const float* __restrict__ eps, const float* __restrict__ pred,
@@ -345,18 +352,19 @@ bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* _
     extern __shared__ __align__(128) uint8_t bn_smem[];
     float* sw = reinterpret_cast<float*>(bn_smem);                                        // [512][64]
     uint32_t* sa = reinterpret_cast<uint32_t*>(bn_smem + (size_t)kFcSlice * 64 * 4);      // [16][256] bf16 pairs
-    float* swd = reinterpret_cast<float*>(bn_smem + kFcSmem);                             // [34][512]
-    __shared__ float part[kFcRows][64];
-    __shared__ float ml_own[2][64];
-    __shared__ float z_own[2][33];
-    __shared__ float z_all[kFcRows][33];
+    float* swd = reinterpret_cast<float*>(bn_smem + (size_t)kFcSlice * 64 * 4 + (size_t)ROWS * kFcSlice * 2);   // [34][512]
+    constexpr int NOWN = (ROWS + kFcSplit - 1) / kFcSplit;     // rows this CTA finishes: rank, rank + 8, ...
+    __shared__ float part[ROWS][64];
+    __shared__ float ml_own[NOWN][64];
+    __shared__ float z_own[NOWN][33];
+    __shared__ float z_all[ROWS][33];
     __shared__ uint64_t bar[2];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int b0 = (blockIdx.x / kFcSplit) * kFcRows, k0 = rank * kFcSlice;
-    const int rows = min(kFcRows, B - b0);
+    const int b0 = (blockIdx.x / kFcSplit) * ROWS, k0 = rank * kFcSlice;
+    const int rows = min(ROWS, B - b0);
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
-    for (int i = threadIdx.x; i < (kFcRows - rows) * (kFcSlice / 2); i += 256) sa[rows * (kFcSlice / 2) + i] = 0u;
+    for (int i = threadIdx.x; i < (ROWS - rows) * (kFcSlice / 2); i += 256) sa[rows * (kFcSlice / 2) + i] = 0u;
     __syncthreads();
     grid_dependency_sync();
     BN_STAMP(0);
@@ -374,24 +382,26 @@ bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* _
     }
     mbar_wait(&bar[0], 0, fault);
     BN_STAMP(1);
-    fc_slice_partial(sa, sw, part);
+    fc_slice_partial<ROWS>(sa, sw, part);
     BN_STAMP(2);
     cluster.sync();
     BN_STAMP(3);
-    if (threadIdx.x < 128) {                     // rows 2 rank, 2 rank + 1: combine the eight K slices in rank order (as fc_fwd_kernel)
-        const int rr = threadIdx.x >> 6, r = rank * 2 + rr, jj = threadIdx.x & 63;
+    if (threadIdx.x < NOWN * 64) {               // rows rank, rank + 8, ..: combine the eight K slices in rank order (as fc_fwd_kernel)
+        const int rr = threadIdx.x >> 6, r = rank + kFcSplit * rr, jj = threadIdx.x & 63;
         float s = 0.f;
+        if (r < ROWS) {
 #pragma unroll
-        for (int q = 0; q < kFcSplit; ++q) s += cluster.map_shared_rank(&part[0][0], q)[r * 64 + jj];
-        s += (jj < 32 ? bmu[jj] : bvar[jj - 32]);
+            for (int q = 0; q < kFcSplit; ++q) s += cluster.map_shared_rank(&part[0][0], q)[r * 64 + jj];
+            s += (jj < 32 ? bmu[jj] : bvar[jj - 32]);
+            if (b0 + r < B) ml[(size_t)(b0 + r) * 64 + jj] = s;
+        }
         ml_own[rr][jj] = s;
-        if (b0 + r < B) ml[(size_t)(b0 + r) * 64 + jj] = s;
     }
     __syncthreads();
-    if (threadIdx.x < 66) {                      // z = mu + eps * exp(logvar / 2) | critic value  (latent_fwd_kernel's expressions)
-        const int rr = threadIdx.x / 33, d = threadIdx.x % 33, r = rank * 2 + rr;
+    if (threadIdx.x < NOWN * 33) {               // z = mu + eps * exp(logvar / 2) | critic value  (latent_fwd_kernel's expressions)
+        const int rr = threadIdx.x / 33, d = threadIdx.x % 33, r = rank + kFcSplit * rr;
         float z = 0.f;
-        if (b0 + r < B) {
+        if (r < ROWS && b0 + r < B) {
             if (d < 32) z = fmaf(__ldg(eps + (size_t)(b0 + r) * 32 + d), expf(0.5f * ml_own[rr][32 + d]), ml_own[rr][d]);
             else z = __ldg(pred + b0 + r);
             zc[(size_t)(b0 + r) * 33 + d] = z;
@@ -399,9 +409,9 @@ bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* _
         z_own[rr][d] = z;
     }
     cluster.sync();
-    for (int i = threadIdx.x; i < kFcRows * 33; i += 256) {
+    for (int i = threadIdx.x; i < ROWS * 33; i += 256) {
         const int r = i / 33, d = i - r * 33;
-        z_all[r][d] = cluster.map_shared_rank(&z_own[0][0], r >> 1)[(r & 1) * 33 + d];
+        z_all[r][d] = cluster.map_shared_rank(&z_own[0][0], r % kFcSplit)[(r / kFcSplit) * 33 + d];
     }
     __syncthreads();
     BN_STAMP(4);
@@ -409,21 +419,21 @@ bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* _
     BN_STAMP(5);
     {   // decoder_input slice: thread -> outputs k0 + 2 tid, + 1 for all 16 rows (decin_fwd_kernel's accumulation order)
         const int kk = 2 * threadIdx.x;
-        float acc0[kFcRows], acc1[kFcRows];
+        float acc0[ROWS], acc1[ROWS];
         const float2 bias = *reinterpret_cast<const float2*>(swd + 33 * kFcSlice + kk);
 #pragma unroll
-        for (int r = 0; r < kFcRows; ++r) { acc0[r] = bias.x; acc1[r] = bias.y; }
+        for (int r = 0; r < ROWS; ++r) { acc0[r] = bias.x; acc1[r] = bias.y; }
         for (int i = 0; i < 33; ++i) {
             const float2 w = *reinterpret_cast<const float2*>(swd + i * kFcSlice + kk);
 #pragma unroll
-            for (int r = 0; r < kFcRows; ++r) {
+            for (int r = 0; r < ROWS; ++r) {
                 const float z = z_all[r][i];
                 acc0[r] = fmaf(w.x, z, acc0[r]);
                 acc1[r] = fmaf(w.y, z, acc1[r]);
             }
         }
 #pragma unroll
-        for (int r = 0; r < kFcRows; ++r)
+        for (int r = 0; r < ROWS; ++r)
             if (b0 + r < B) *reinterpret_cast<uint32_t*>(h + (size_t)(b0 + r) * 4096 + k0 + kk) = pack_bf16x2(acc0[r], acc1[r]);
     }
     BN_STAMP(6);
@@ -432,8 +442,10 @@ bottleneck_fwd_kernel(int B, const __nv_bfloat16* __restrict__ a, const float* _
     bn_wall(1);
 }
 
-static constexpr size_t kBnBwdSmem = kDdSmem + (size_t)kDdSlice * 64 * 4;      // decoder_input operands + this CTA's [512][64] fc slice
-__global__ void __cluster_dims__(kDdSplit, 1, 1) __launch_bounds__(256)
+// decoder_input operands + this CTA's [512][64] fc slice; ROWS * 16 threads (one (row, output pair) per thread in the first phase)
+template <int ROWS> constexpr size_t bn_bwd_smem() { return (size_t)33 * kDdWStride * 4 + (size_t)ROWS * kDdSlice * 2 + (size_t)kDdSlice * 64 * 4; }
+template <int ROWS>
+__global__ void __cluster_dims__(kDdSplit, 1, 1) __launch_bounds__(ROWS * 16)
 bottleneck_bwd_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* __restrict__ wdec, const float* __restrict__ ml,
                       const float* __restrict__ eps, float kld_grad_scale, const float* __restrict__ wfc, float* __restrict__ dzc,
                       float* __restrict__ dml, __nv_bfloat16* __restrict__ da, int* fault) {
@@ -441,18 +453,19 @@ bottleneck_bwd_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* 
     extern __shared__ __align__(128) uint8_t bb_smem[];
     float* sw = reinterpret_cast<float*>(bb_smem);                                            // [33][516]
     uint32_t* sd = reinterpret_cast<uint32_t*>(bb_smem + (size_t)33 * kDdWStride * 4);         // [16][256] bf16 pairs
-    float* swf = reinterpret_cast<float*>(bb_smem + kDdSmem);                                  // [512][64] rows k0 .. of wfc
-    __shared__ float part[kDdRows][33];
-    __shared__ float dz_own[2][33];
-    __shared__ float dml_own[2][64];
-    __shared__ __align__(16) float dml_all[kDdRows][64];
+    float* swf = reinterpret_cast<float*>(bb_smem + (size_t)33 * kDdWStride * 4 + (size_t)ROWS * kDdSlice * 2);   // [512][64] rows k0 .. of wfc
+    constexpr int NOWN = (ROWS + kDdSplit - 1) / kDdSplit, kThreads = ROWS * 16;
+    __shared__ float part[ROWS][33];
+    __shared__ float dz_own[NOWN][33];
+    __shared__ float dml_own[NOWN][64];
+    __shared__ __align__(16) float dml_all[ROWS][64];
     __shared__ uint64_t bar, bar_w;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int b0 = (blockIdx.x / kDdSplit) * kDdRows, k0 = rank * kDdSlice;
-    const int rows = min(kDdRows, B - b0);
+    const int b0 = (blockIdx.x / kDdSplit) * ROWS, k0 = rank * kDdSlice;
+    const int rows = min(ROWS, B - b0);
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar_w, 1); mbar_fence_init(); }
-    for (int i = threadIdx.x; i < (kDdRows - rows) * (kDdSlice / 2); i += 256) sd[rows * (kDdSlice / 2) + i] = 0u;
+    for (int i = threadIdx.x; i < (ROWS - rows) * (kDdSlice / 2); i += kThreads) sd[rows * (kDdSlice / 2) + i] = 0u;
     __syncthreads();
     grid_dependency_sync();
     BN_STAMP(8);
@@ -474,19 +487,21 @@ bottleneck_bwd_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* 
     BN_STAMP(10);
     cluster.sync();
     BN_STAMP(11);
-    if (threadIdx.x < 66) {                      // rows 2 rank, 2 rank + 1 (as decin_bwd_data_kernel)
-        const int rr = threadIdx.x / 33, r = rank * 2 + rr, i = threadIdx.x % 33;
+    if (threadIdx.x < NOWN * 33) {               // rows rank, rank + 8, .. (as decin_bwd_data_kernel)
+        const int rr = threadIdx.x / 33, r = rank + kDdSplit * rr, i = threadIdx.x % 33;
         float sacc = 0.f;
+        if (r < ROWS) {
 #pragma unroll
-        for (int q = 0; q < kDdSplit; ++q) sacc += cluster.map_shared_rank(&part[0][0], q)[r * 33 + i];
+            for (int q = 0; q < kDdSplit; ++q) sacc += cluster.map_shared_rank(&part[0][0], q)[r * 33 + i];
+            if (dzc && b0 + r < B) dzc[(size_t)(b0 + r) * 33 + i] = sacc;
+        }
         dz_own[rr][i] = sacc;
-        if (dzc && b0 + r < B) dzc[(size_t)(b0 + r) * 33 + i] = sacc;
     }
     __syncthreads();
-    if (threadIdx.x < 64) {                      // reparametrise backward + KL gradient (latent_bwd_kernel's expressions, no external terms)
-        const int rr = threadIdx.x >> 5, d = threadIdx.x & 31, r = rank * 2 + rr;
+    if (threadIdx.x < NOWN * 32) {               // reparametrise backward + KL gradient (latent_bwd_kernel's expressions, no external terms)
+        const int rr = threadIdx.x >> 5, d = threadIdx.x & 31, r = rank + kDdSplit * rr;
         float om = 0.f, ol = 0.f;
-        if (b0 + r < B) {
+        if (r < ROWS && b0 + r < B) {
             const float mu = __ldg(ml + (size_t)(b0 + r) * 64 + d), lv = __ldg(ml + (size_t)(b0 + r) * 64 + 32 + d);
             const float e = __ldg(eps + (size_t)(b0 + r) * 32 + d), dz = dz_own[rr][d];
             const float std_ = expf(0.5f * lv);
@@ -503,22 +518,22 @@ bottleneck_bwd_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* 
         dml_own[rr][32 + d] = ol;
     }
     cluster.sync();
-    for (int i = threadIdx.x; i < kDdRows * 64; i += 256) {
+    for (int i = threadIdx.x; i < ROWS * 64; i += kThreads) {
         const int r = i >> 6, j = i & 63;
-        dml_all[r][j] = cluster.map_shared_rank(&dml_own[0][0], r >> 1)[(r & 1) * 64 + j];
+        dml_all[r][j] = cluster.map_shared_rank(&dml_own[0][0], r % kDdSplit)[(r / kDdSplit) * 64 + j];
     }
     __syncthreads();
     BN_STAMP(12);
     mbar_wait(&bar_w, 0, fault);
-    {   // (fc_mu || fc_var)^T slice: thread -> k' = k0 + 2 tid, + 1, all 16 rows, weight rows from shared memory
+    if (threadIdx.x < 256) {   // (fc_mu || fc_var)^T slice: thread -> k' = k0 + 2 tid, + 1, all rows, weight rows from shared memory
         const int kl = 2 * threadIdx.x, kp = k0 + kl, rot = (kp >> 1) & 15;
-        float acc0[kDdRows], acc1[kDdRows];
+        float acc0[ROWS], acc1[ROWS];
 #pragma unroll
-        for (int r = 0; r < kDdRows; ++r) acc0[r] = acc1[r] = 0.f;
-        fc_bwd_rows<kDdRows, true>(reinterpret_cast<const float4*>(swf + (size_t)kl * 64), rot, dml_all, acc0);
-        fc_bwd_rows<kDdRows, true>(reinterpret_cast<const float4*>(swf + (size_t)(kl + 1) * 64), rot, dml_all, acc1);
+        for (int r = 0; r < ROWS; ++r) acc0[r] = acc1[r] = 0.f;
+        fc_bwd_rows<ROWS, true>(reinterpret_cast<const float4*>(swf + (size_t)kl * 64), rot, dml_all, acc0);
+        fc_bwd_rows<ROWS, true>(reinterpret_cast<const float4*>(swf + (size_t)(kl + 1) * 64), rot, dml_all, acc1);
 #pragma unroll
-        for (int r = 0; r < kDdRows; ++r)
+        for (int r = 0; r < ROWS; ++r)
             if (b0 + r < B) *reinterpret_cast<uint32_t*>(da + (size_t)(b0 + r) * 4096 + kp) = pack_bf16x2(acc0[r], acc1[r]);
     }
     BN_STAMP(13);
@@ -531,9 +546,55 @@ bottleneck_bwd_kernel(int B, const __nv_bfloat16* __restrict__ dh, const float* 
 
 using namespace cvae;
 
+// How many 8-CTA clusters of a kernel the device holds at once (cudaOccupancyMaxActiveClusters; 15 on a B200 at one CTA
+// per SM), cached per kernel.  The fused kernels pick 20 rows per cluster when 16 would need one cluster too many.
+template <typename K>
+static int max_clusters_of(K kern, int threads, size_t smem) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(128);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = -1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
+// rows per cluster: 16 unless that needs more clusters than fit at once and 20 does not
+static int bottleneck_rows(int batch, int max_clusters) {
+    if (const char* e = getenv("CVAE_BOTTLENECK_ROWS")) return atoi(e) == 20 ? 20 : 16;      // (experiments)
+    if (max_clusters <= 0) return 16;
+    const int c16 = (batch + 15) / 16, c20 = (batch + 19) / 20;
+    return (c16 > max_clusters && c20 <= max_clusters) ? 20 : 16;
+}
+
+// profiling aid: 8-CTA clusters of the forward (which = 0) / backward (1) kernel (16-row form) the device holds at once with
+// `smem` bytes of dynamic shared memory per CTA (0: the kernel's own size); negative on error
+extern "C" int cvae_bottleneck_max_clusters(int which, int64_t smem) {
+    if (which) {
+        CVAE_OPT_IN_SMEM(bottleneck_bwd_kernel<16>, bn_bwd_smem<16>());
+        return max_clusters_of(bottleneck_bwd_kernel<16>, 256, smem > 0 ? (size_t)smem : bn_bwd_smem<16>());
+    }
+    CVAE_OPT_IN_SMEM(bottleneck_fwd_kernel<16>, bn_fwd_smem<16>());
+    return max_clusters_of(bottleneck_fwd_kernel<16>, 256, smem > 0 ? (size_t)smem : bn_fwd_smem<16>());
+}
+
 extern "C" int cvae_bottleneck_debug(void* device_buf16) {
     long long* p = (long long*)device_buf16;
     CVAE_CUDA(cudaMemcpyToSymbol(g_bn_dbg, &p, sizeof(p)));
+    return CVAE_OK;
+}
+
+template <int ROWS>
+static int launch_bottleneck_fwd(int batch, const void* act, const float* wfc, const float* bias_mu, const float* bias_var, const float* eps,
+                                 const float* pred, const float* wdec, float* mu_logvar, float* z_pred, void* dec_in, int* fault, cudaStream_t stream) {
+    CVAE_OPT_IN_SMEM(bottleneck_fwd_kernel<ROWS>, bn_fwd_smem<ROWS>());
+    cvae::launch(bottleneck_fwd_kernel<ROWS>, ((batch + ROWS - 1) / ROWS) * kFcSplit, 256, bn_fwd_smem<ROWS>(), stream, batch, (const __nv_bfloat16*)act,
+                 wfc, bias_mu, bias_var, eps, pred, wdec, mu_logvar, z_pred, (__nv_bfloat16*)dec_in, fault);
+    CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
 
@@ -545,11 +606,24 @@ extern "C" int cvae_bottleneck_fwd(int batch, const void* act, const float* wfc,
     cudaStream_t stream = (cudaStream_t)stream_;
     CVAE_REQUIRE(batch > 0 && act && wfc && bias_mu && bias_var && eps && pred && wdec && mu_logvar && z_pred && dec_in, CVAE_EINVAL,
                  "bottleneck_fwd: bad argument");
-    CVAE_OPT_IN_SMEM(bottleneck_fwd_kernel, kBnFwdSmem);
     int* fault = fault_flag();
     CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "bottleneck_fwd: fault flag unavailable");
-    cvae::launch(bottleneck_fwd_kernel, ((batch + kFcRows - 1) / kFcRows) * kFcSplit, 256, kBnFwdSmem, stream, batch, (const __nv_bfloat16*)act, wfc,
-                 bias_mu, bias_var, eps, pred, wdec, mu_logvar, z_pred, (__nv_bfloat16*)dec_in, fault);
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        CVAE_OPT_IN_SMEM(bottleneck_fwd_kernel<16>, bn_fwd_smem<16>());
+        max_clusters = max_clusters_of(bottleneck_fwd_kernel<16>, 256, bn_fwd_smem<16>());
+    }
+    if (bottleneck_rows(batch, max_clusters) == 20)
+        return launch_bottleneck_fwd<20>(batch, act, wfc, bias_mu, bias_var, eps, pred, wdec, mu_logvar, z_pred, dec_in, fault, stream);
+    return launch_bottleneck_fwd<16>(batch, act, wfc, bias_mu, bias_var, eps, pred, wdec, mu_logvar, z_pred, dec_in, fault, stream);
+}
+
+template <int ROWS>
+static int launch_bottleneck_bwd(int batch, const void* d_dec_in, const float* wdec, const float* mu_logvar, const float* eps, float kld_grad_scale,
+                                 const float* wfc, float* d_z_pred, float* d_mu_logvar, void* d_act, int* fault, cudaStream_t stream) {
+    CVAE_OPT_IN_SMEM(bottleneck_bwd_kernel<ROWS>, bn_bwd_smem<ROWS>());
+    cvae::launch(bottleneck_bwd_kernel<ROWS>, ((batch + ROWS - 1) / ROWS) * kDdSplit, ROWS * 16, bn_bwd_smem<ROWS>(), stream, batch,
+                 (const __nv_bfloat16*)d_dec_in, wdec, mu_logvar, eps, kld_grad_scale, wfc, d_z_pred, d_mu_logvar, (__nv_bfloat16*)d_act, fault);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
@@ -561,13 +635,16 @@ extern "C" int cvae_bottleneck_bwd(int batch, const void* d_dec_in, const float*
                                    void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CVAE_REQUIRE(batch > 0 && d_dec_in && wdec && mu_logvar && eps && wfc && d_mu_logvar && d_act, CVAE_EINVAL, "bottleneck_bwd: bad argument");
-    CVAE_OPT_IN_SMEM(bottleneck_bwd_kernel, kBnBwdSmem);
     int* fault = fault_flag();
     CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "bottleneck_bwd: fault flag unavailable");
-    cvae::launch(bottleneck_bwd_kernel, ((batch + kDdRows - 1) / kDdRows) * kDdSplit, 256, kBnBwdSmem, stream, batch, (const __nv_bfloat16*)d_dec_in,
-                 wdec, mu_logvar, eps, kld_grad_scale, wfc, d_z_pred, d_mu_logvar, (__nv_bfloat16*)d_act, fault);
-    CVAE_LAUNCH_CHECK();
-    return CVAE_OK;
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        CVAE_OPT_IN_SMEM(bottleneck_bwd_kernel<16>, bn_bwd_smem<16>());
+        max_clusters = max_clusters_of(bottleneck_bwd_kernel<16>, 256, bn_bwd_smem<16>());
+    }
+    if (bottleneck_rows(batch, max_clusters) == 20)
+        return launch_bottleneck_bwd<20>(batch, d_dec_in, wdec, mu_logvar, eps, kld_grad_scale, wfc, d_z_pred, d_mu_logvar, d_act, fault, stream);
+    return launch_bottleneck_bwd<16>(batch, d_dec_in, wdec, mu_logvar, eps, kld_grad_scale, wfc, d_z_pred, d_mu_logvar, d_act, fault, stream);
 }
 
 extern "C" int cvae_fc_fwd(int batch, const void* act, const float* wfc, const float* bias_mu,

@@ -221,6 +221,9 @@ int cvae_bottleneck_fwd(int batch, const void* act, const float* wfc, const floa
 /* profiling aid: device buffer of 16 + 4 * CTAs int64; CTA 0 of the two kernels stamps clock64() at its phase boundaries,
  * every CTA %globaltimer at entry and exit (NULL = off) */
 int cvae_bottleneck_debug(void* device_buf16);
+/* profiling aid: 8-CTA clusters of the forward (0) / backward (1) kernel the device holds at once with `smem` dynamic
+ * bytes per CTA (0: the kernel's own) */
+int cvae_bottleneck_max_clusters(int which, int64_t smem);
 int cvae_bottleneck_bwd(int batch, const void* d_dec_in, const float* wdec, const float* mu_logvar, const float* eps,
                         float kld_grad_scale, const float* wfc, float* d_z_pred, float* d_mu_logvar, void* d_act,
                         void* stream);

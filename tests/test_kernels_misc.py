@@ -200,7 +200,7 @@ def test_linear_layers(B):
     close(from_nhwc(da), a_req.grad, tol=1e-2)
 
 
-@pytest.mark.parametrize("B", [1, 19, 64, 256])
+@pytest.mark.parametrize("B", [1, 19, 64, 256, 290])      # 256, 290: 20 rows per cluster (16 would need a 16th+ cluster, a second wave)
 def test_bottleneck_fused_equals_the_three_separate_kernels(B):
     """cvae_bottleneck_fwd / _bwd (one launch per direction, the training path) against fc -> latent -> decoder_input and
     their data gradients run one by one (checked against torch above): bit for bit, including ragged row blocks."""

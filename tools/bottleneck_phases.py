@@ -42,7 +42,11 @@ names_b = ["start", "operands landed", "decin partial done", "cluster sync 1", "
 print("forward (cycles since start of CTA 0):", [(n, t[i] - t[0]) for i, n in enumerate(names_f)])
 print("backward:", [(n, t[8 + i] - t[8]) for i, n in enumerate(names_b)])
 w = dbg[16:].view(128, 4).cpu().double()
+w = w[w[:, 0] > 0]                       # CTAs that ran (13 clusters of 20 rows at batch 256)
+print("CTAs:", w.shape[0])
 for name, a, b in (("forward", 0, 1), ("backward", 2, 3)):
     t0 = w[:, a].min()
     print(f"{name}: CTA entry {((w[:, a] - t0).min() / 1e3):.1f} .. {((w[:, a] - t0).max() / 1e3):.1f} us, exit {((w[:, b] - t0).min() / 1e3):.1f} .. "
           f"{((w[:, b] - t0).max() / 1e3):.1f} us, CTA 0 lives {(w[0, b] - w[0, a]) / 1e3:.1f} us")
+for which, name in ((0, "forward"), (1, "backward")):
+    print(name, "max active 8-CTA clusters:", {kb: L.lib.cvae_bottleneck_max_clusters(which, kb * 1024) for kb in (0, 48, 100, 112, 150, 200)})
