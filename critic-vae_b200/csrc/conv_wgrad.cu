@@ -270,7 +270,12 @@ __device__ __forceinline__ float fold_term(const FoldArgs& f, const float* __res
             acc += __ldg(p + ((size_t)t * f.m_total + ab * f.cout + co) * f.n + ci);
         }
         return acc;
-    } else if (f.kind == CVAE_WGRAD_SHIFT_FRAMES) {  // group = ky, row = (kx, ch), col = co
+    } else if (f.kind == CVAE_WGRAD_SHIFT_FRAMES) {
+        if (f.stack) {   // launch_wgrad_frames: group 0 = filter rows 3..0 as row blocks 0..3 of 32 channels, group 1 = row 4; col = (kx, ch)
+            const int g = ky < 4 ? 0 : 1, j = ky < 4 ? 3 - ky : 0;
+            return __ldg(p + ((size_t)g * f.m_total + j * f.cout + co) * f.n + kx * 8 + ci);
+        }
+        // group = ky, row = (kx, ch), col = co
         return __ldg(p + ((size_t)ky * f.m_total + kx * 8 + ci) * f.n + co);
     } else {  // CVAE_WGRAD_SHIFT_PHASE12: group = (plane p, ty), row = (j, e), col = ci; tx = 1 - j
         float acc = 0.f;
@@ -476,6 +481,12 @@ struct WgTmaArgs {
     int a_kstep, b_kstep;       // descriptor units (16 B) per K = 16 step: 128 for 128-byte rows, 64 for 64-byte rows
     int b_row_units;            // 16-byte units per B row (8 or 4)
     uint32_t a_hi, b_hi;        // high descriptor words (SBO, version, swizzle type) of A and B
+    // Frame-operand variant (launch_wgrad_frames, encoder conv 0): B is not a TMA tile but one no-swizzle plane
+    // [virtual pixel][3 frame channels + 5 zeros] that the eight epilogue warps convert from the fp32 NCHW frames
+    // themselves while the GEMM runs (b_fill = 1, b_blocks = 0); column block i of B is that plane one pixel further on.
+    int b_fill, b_count, b_pad_rows;   // slots per chunk; virtual rows above each image in the plane's pixel numbering
+    PlaneSrc pb;
+    FastDiv dPW, dIH;
     int ones_off, ones_stride;  // bias pseudo-group operand: no-swizzle plane pair of ones after the buffers (0: none)
     int m_rows, groups_total, gpc, split_floats;
     int tap_row[kMaxGroups];    // dy * PW + dx per group
@@ -499,7 +510,7 @@ conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap map
     const int g0 = gset * a.gpc, g1 = min(g0 + a.gpc, a.groups_total);
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], a.b_fill ? 1 + (kWtThreads / 32 - 2) : 1); mbar_init(&bar_empty[i], 1); }
         mbar_init(&bar_acc, 1);
         mbar_fence_init();
     }
@@ -613,6 +624,25 @@ conv_wgrad_tma_kernel(const WgTmaArgs a, const __grid_constant__ CUtensorMap map
         }
         __syncwarp();
     } else {
+        if (a.b_fill) {
+            // ------------------------------ B plane loaders (the epilogue warps, idle until the last chunk) ------------
+            bool alive = true;
+            const int ltid = tid - 64;
+            for (int i = 0; i < my_chunks && alive; ++i) {
+                const int buf = i % a.nbuf;
+                const int chunk = split + i * a.splits;
+                alive = mbar_wait(&bar_empty[buf], ((i / a.nbuf) & 1) ^ 1, a.fault);
+                const int n = chunk / a.blocks_per_image;
+                const int ha = (chunk - n * a.blocks_per_image) * a.RA - a.a_row0;
+                // slot 0 = frame pixel (row ha + 1, column -2) of image n: the first tap of group 0 for A row 0
+                const int v_first = (n * a.pb.IH + ha + 1 + a.b_pad_rows) * a.pb.PW - 2;
+                fill_planes<CVAE_LOAD_NCHW3>(a.pb, a.dPW, a.dIH, smem + (size_t)buf * a.buf_bytes + a.a_region, 0, v_first, a.b_count, ltid,
+                                             kWtThreads - 64);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[buf]);
+            }
+        }
         // ------------------------------ epilogue (8 warps: lane quarter = warp % 4, groups dealt by parity) -------------
         mbar_wait(&bar_acc, 0, a.fault);
         tc_fence_after();
@@ -912,6 +942,112 @@ static int launch_wgrad_stack(const cvae_wgrad_desc* d, int H, int W, int pad, c
     return CVAE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Encoder conv 0 (3 -> 32 channels, 64x64 frames): dW[co][ch][ky][kx] = sum_q dY[q][co] * F[q + (ky - 2) PW + kx - 2][ch].
+// The plane kernel runs it as 5 MMAs of N = 32 per K step with 15 useful rows out of 128 (16 pixel shifts x 8 channel
+// slots) and is bound by the N = 32 MMA rate (profiles/r02_e0w_counters.log: 117 k cycles, 9 k of them waiting for data).
+// Here the roles are swapped and both operands are stacked:
+//   A = dY, TMA box of [virtual pixel][32 co] rows (64 B, SWIZZLE_64B); its four 32-row blocks are the SAME tile 0, 1, 2, 3
+//       image rows further on (LBO = PW x 64 B), i.e. filter rows ky_g, ky_g - 1, ky_g - 2, ky_g - 3;
+//   B = the frames as ONE no-swizzle plane [virtual pixel][3 ch + 5 zeros], converted from fp32 NCHW by the epilogue warps;
+//       its six 8-column blocks are the plane 0..5 pixels further on (SBO = 16 B), i.e. kx = 0..4 (+ one unused).
+// Two MMAs of N = 48 per K step (ky_g = 3: filter rows 3..0; ky_g = 4: row 4 in block 0) instead of five of N = 32.
+// Chunks are RA image rows starting three rows early (all four blocks see every row once); RA x PW is a multiple of 16.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kFramesN = 48, kFramesGroups = 2;
+static bool wgrad_frames_shape(const cvae_wgrad_desc* d) {
+    return d->kind == CVAE_WGRAD_SHIFT_FRAMES && d->cout == 32 && d->cin == 3 && d->dbias == nullptr;
+}
+
+static int launch_wgrad_frames(const cvae_wgrad_desc* d, int H, int W, int pad, cudaStream_t stream, int max_splits, int* splits_out) {
+    if (g_wg_no_tma || g_wg_no_stack || !wgrad_frames_shape(d) || !tensor_map_encoder()) return 1;
+    WgTmaArgs t{};
+    t.pad = pad;
+    t.rows_mode = 1; t.NB = 1;
+    t.b_blocks = 0;                                  // no TMA for B
+    t.b_fill = 1;
+    t.a_row0 = 3;
+    t.a_loads = 1;
+    const int pad_rows = 16;                         // virtual rows above each image in the plane's pixel numbering (>= every overshoot)
+    const size_t cap = 212 * 1024;
+    int splits = max_splits < 1 ? 1 : max_splits;
+    int best_pw = 0, best_ra = 0;
+    double best_cost = 1e30;
+    int PW = 0;
+    auto plan = [&](int pw, int RA) -> bool {
+        const int kc = RA * pw;
+        if ((kc & 15) || pw > 256 || RA + 3 > 256) return false;
+        const int a_region = (((RA + 3) * pw * 64) + 1023) & ~1023;
+        const int b_count = (kc + pw + 5 + 3 + 15) & ~15;
+        const int b_bytes = (b_count * 16 + 1023) & ~1023;
+        const size_t buf = (size_t)a_region + b_bytes;
+        if (2 * buf > cap || a_region >= (1 << 18)) return false;
+        int nbuf = (int)(cap / buf);
+        t.nbuf = nbuf > 4 ? 4 : nbuf;
+        t.RA = RA; t.kc = kc;
+        t.a_block_bytes = pw * 64;                   // LBO of A: the next 32-row block is the next image row
+        t.a_region = a_region;
+        t.b_block_bytes = 128;                       // LBO of B (no swizzle): 8 pixels of 16 B along K
+        t.b_count = b_count;
+        t.buf_bytes = (int)buf;
+        t.tx_bytes = (uint32_t)((RA + 3) * pw * 64);
+        t.blocks_per_image = (H + 3 + RA - 1) / RA;
+        t.num_chunks = d->batch * t.blocks_per_image;
+        PW = pw;
+        return true;
+    };
+    for (int pw = W + pad; pw <= W + pad + 8; ++pw)
+        for (int RA = 1; RA <= H + 3; ++RA) {
+            if (!plan(pw, RA)) continue;
+            if ((t.blocks_per_image - 1) * RA - 3 + 1 + (t.kc + pw + 8) / pw + 1 - H >= pad_rows) continue;   // rows below the image must stay virtual
+            const int per_cta = (t.num_chunks + splits - 1) / splits;
+            double cost = (double)per_cta * (t.kc + 64);
+            if (per_cta < 2) cost *= 2.0;
+            if (cost < best_cost) { best_cost = cost; best_pw = pw; best_ra = RA; }
+        }
+    if (g_wg_stack_pw > 0 && g_wg_stack_ra > 0 && plan(W + pad + g_wg_stack_pw - 1, g_wg_stack_ra)) { best_pw = W + pad + g_wg_stack_pw - 1; best_ra = g_wg_stack_ra; }
+    if (best_pw == 0 || !plan(best_pw, best_ra)) return 1;
+    if (splits > t.num_chunks) splits = t.num_chunks;
+    t.splits = splits;
+
+    CUtensorMap mA[4], mB;
+    if (!encode_map_4d(&mA[0], d->dy, d->cout, W, H, d->batch, d->cout, (long)W * d->cout, (long)H * W * d->cout, 32, PW, t.RA + 3, 1,
+                       CU_TENSOR_MAP_SWIZZLE_64B))
+        return 1;
+    mA[1] = mA[2] = mA[3] = mB = mA[0];
+    t.phase_maps = 0;
+    t.a_kstep = 64;
+    t.a_hi = (512u >> 4) | (1u << 14) | (4u << 29);  // SBO 512 B (8 rows of 64 B), version 1, SWIZZLE_64B
+    t.b_kstep = 16; t.b_row_units = 1;               // plane slots of 16 B
+    t.b_hi = (16u >> 4) | (1u << 14);                // SBO 16 B: the next 8 columns are the plane one pixel on; no swizzle
+    t.b_box_row = 0; t.b_base_row = 0;
+    t.b_pad_rows = pad_rows;
+    t.pb = PlaneSrc{d->batch, H, W, pad_rows, PW, H + pad_rows, 1, 3, 0, d->x, nullptr};
+    t.dPW = make_fastdiv(PW);
+    t.dIH = make_fastdiv(H + pad_rows);
+
+    t.m_rows = 128;
+    t.groups_total = kFramesGroups;
+    t.gpc = kFramesGroups;
+    t.split_floats = kFramesGroups * 128 * kFramesN;
+    for (int g = 0; g < kFramesGroups; ++g) {
+        t.gn[g] = kFramesN;
+        t.gout[g] = g * 128 * kFramesN;
+        t.tap_row[g] = g * PW;                       // group 1's block 0 is one filter row further down
+    }
+    t.partial = (float*)d->workspace; t.fault = fault_flag();
+    if (t.fault == nullptr) return 1;
+    const size_t smem = (size_t)t.nbuf * t.buf_bytes;
+    CVAE_OPT_IN_SMEM(conv_wgrad_tma_kernel, smem);
+    if (g_wg_debug)
+        fprintf(stderr, "conv_wgrad_frames %dx%d: PW=%d RA=%d kc=%d nbuf=%d chunks=%d splits=%d buf=%d smem=%zu\n", H, W, PW, t.RA, t.kc, t.nbuf,
+                t.num_chunks, splits, t.buf_bytes, smem);
+    cvae::launch(conv_wgrad_tma_kernel, dim3(splits, 1, 1), kWtThreads, smem, stream, t, mA[0], mA[1], mA[2], mA[3], mB);
+    CVAE_LAUNCH_CHECK();
+    *splits_out = splits;
+    return CVAE_OK;
+}
+
 }  // namespace cvae
 
 using namespace cvae;
@@ -971,6 +1107,10 @@ static int64_t wgrad_workspace_exact(const cvae_wgrad_desc* d) {
     WgShape s;
     if (!wgrad_shape(d, s)) return -1;
     int64_t bytes = (int64_t)s.max_splits * s.split_floats * 4;   // the plane and the TMA variant use <= max_splits splits
+    if (wgrad_frames_shape(d)) {
+        const int64_t sb = (int64_t)(d->splits > 0 ? d->splits : sm_count()) * kFramesGroups * 128 * kFramesN * 4;
+        if (sb > bytes) bytes = sb;
+    }
     WgStackShape st;
     if (wgrad_stack_shape(d, st)) {                               // the tap-stacked variant: one CTA per SM, wider partials
         const int64_t sb = (int64_t)(d->splits > 0 ? d->splits : sm_count()) * st.split_floats * 4;
@@ -1154,7 +1294,17 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
     int stack_splits = 0, stack_bias_off = -1;
     int rc = launch_wgrad_stack(d, H, W, pad, stream, d->splits > 0 ? d->splits : sm_count(), stack, &stack_splits, &stack_bias_off);
     if (rc < 0) return rc;
-    const bool stacked = rc == CVAE_OK;
+    bool stacked = rc == CVAE_OK;
+    bool frames_stacked = false;
+    if (!stacked) {
+        rc = launch_wgrad_frames(d, H, W, pad, stream, d->splits > 0 ? d->splits : sm_count(), &stack_splits);
+        if (rc < 0) return rc;
+        if (rc == CVAE_OK) {
+            stacked = frames_stacked = true;
+            stack.n = kFramesN;
+            stack.split_floats = kFramesGroups * 128 * kFramesN;
+        }
+    }
     int tma_splits = shape.max_splits;
     if (!stacked) rc = launch_wgrad_tma(d, a, n, gsets, H, W, pad, stream, &tma_splits);
     if (rc < 0) return rc;
@@ -1199,7 +1349,9 @@ extern "C" int cvae_conv_wgrad(const cvae_wgrad_desc* d, void* stream_) {
             else CVAE_FOLD_ROWS(2)
 #undef CVAE_FOLD_ROWS
         } else {
-            cvae::launch(wgrad_fold_kernel<8>, (total + 31) / 32, 256, 0, stream, f);
+            // few outputs (2.4 k), many splits: 32 split lanes per output keep the chain of dependent loads short (this fold
+            // of encoder conv 0 is the last kernel in front of the optimizer)
+            cvae::launch(wgrad_fold_kernel<32>, (total + 7) / 8, 256, 0, stream, f);
         }
     }
     CVAE_LAUNCH_CHECK();

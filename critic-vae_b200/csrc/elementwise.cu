@@ -558,16 +558,32 @@ extern "C" int cvae_frames_u8_to_f32(int frames, const uint8_t* hwc_u8, float* n
     return CVAE_OK;
 }
 
+extern "C" int cvae_adam_update(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale, int tick,
+                                void* stream);
+
 extern "C" int cvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                               int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale,
                               void* stream) {
+    return cvae_adam_update(n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale, 1, stream);
+}
+
+// One Adam update of a RANGE of the flat buffers (all four pointers offset alike, 16-byte aligned) with the step count the
+// device counter will have after this optimizer step; `tick` != 0 advances the counter afterwards.  A step may be applied
+// in several ranges (the training step updates everything but the first conv block while that block's gradient is still
+// being computed): every range but the last passes tick = 0.
+extern "C" int cvae_adam_update(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale, int tick,
+                                void* stream) {
     CVAE_REQUIRE(n > 0 && params && grads && exp_avg && exp_avg_sq && step, CVAE_EINVAL, "adam_step: bad argument");
     CVAE_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, CVAE_EINVAL,
                  "adam_step: the flat buffers must be 16-byte aligned");
     cvae::launch(adam_kernel, grid_for((n + 3) / 4, 256, 16), 256, 0, (cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq,
                                                                     (const long long*)step, lr, beta1, beta2, eps, grad_scale);
     CVAE_LAUNCH_CHECK();
-    cvae::launch(adam_tick_kernel, 1, 1, 0, (cudaStream_t)stream, (long long*)step);
-    CVAE_LAUNCH_CHECK();
+    if (tick) {
+        cvae::launch(adam_tick_kernel, 1, 1, 0, (cudaStream_t)stream, (long long*)step);
+        CVAE_LAUNCH_CHECK();
+    }
     return CVAE_OK;
 }

@@ -140,6 +140,9 @@ class VAEEngine:
         self.early_event = None     # optional torch.cuda.Event(external=True) recorded when the early gradient bucket is final
         # the three layers around the latent as one launch per direction in the training step (CVAE_NO_FUSED_BOTTLENECK=1: six launches)
         self.fused_bottleneck = os.environ.get("CVAE_NO_FUSED_BOTTLENECK") is None
+        self.early_adam = None      # dict(lr=, grad_scale=): update all parameters but the first conv block inside backward()
+        self.adam_stream = None
+        self._adam_used = False
 
     # ---- parameters ---------------------------------------------------------------------------
     def view(self, name, buf=None):
@@ -400,13 +403,32 @@ class VAEEngine:
             launch(L.stream_ptr())
         self._side_used = True
 
+    def _early_adam_launch(self):
+        """Every gradient except encoder conv 0's is final once the main, side and fold streams reach this point: update
+        those parameters on a stream of their own, beside the last weight-gradient GEMM (which runs alone at the end of
+        the step otherwise, with the whole optimizer waiting behind it).  Single-GPU training step only (TrainStep sets
+        self.early_adam = dict(lr=, grad_scale=) around backward(); the caller finishes with adam_step(hi=first_block_end()))."""
+        if self.adam_stream is None:
+            self.adam_stream = torch.cuda.Stream()
+        st = self.adam_stream
+        st.wait_stream(torch.cuda.current_stream())
+        if self._side_used:
+            st.wait_stream(self.side_stream)
+        if self._fold_used:
+            st.wait_stream(self.fold_stream)
+        with torch.cuda.stream(st):
+            self.adam_step(lo=self.first_block_end(), tick=False, **self.early_adam)
+        self._adam_used = True
+
     def _join_leaves(self):
         """Wait (on the current stream) for the parameter-gradient launches that ran on the side / fold streams."""
         if self._side_used:
             torch.cuda.current_stream().wait_stream(self.side_stream)
         if self._fold_used:
             torch.cuda.current_stream().wait_stream(self.fold_stream)
-        self._side_used = self._fold_used = False
+        if self._adam_used:
+            torch.cuda.current_stream().wait_stream(self.adam_stream)
+        self._side_used = self._fold_used = self._adam_used = False
 
     def early_bucket_offset(self):
         """The flat gradient splits into [encoder convolutions + BatchNorm | everything else]: the second part (the two
@@ -494,6 +516,8 @@ class VAEEngine:
                                                _ptr(ws.bn_sums), _ptr(ws.g_c[i]), _ptr(G(bname + ".weight")),
                                                _ptr(G(bname + ".bias")), s))
             if i == 0:
+                if self.early_adam is not None and self.side_stream is not None and self.profile is None and g is self.gflat:
+                    self._early_adam_launch()
                 self._wgrad(g, cname, kind=L.WGRAD_SHIFT_FRAMES, batch=B, height=64, width=64, cout=32, cin=3, x=x, dy=ws.g_c[0])
             else:
                 self._wgrad(g, cname, kind=L.WGRAD_5X5, batch=B, height=h, width=h, cout=co, cin=ci, x=ws.a[i - 1], dy=ws.g_c[i])
@@ -502,12 +526,20 @@ class VAEEngine:
 
     # ---- optimizer ----------------------------------------------------------------------------
     @_nvtx("adam")
-    def adam_step(self, lr, grad_scale=1.0, betas=(0.9, 0.999), eps=1e-8, g=None):
+    def adam_step(self, lr, grad_scale=1.0, betas=(0.9, 0.999), eps=1e-8, g=None, lo=0, hi=None, tick=True):
+        """torch.optim.Adam's update (vae.py:36, :56) of the flat parameters [lo, hi) (default: all of them); `tick` advances
+        the device step counter -- a step applied in several ranges ticks with the last one only."""
         if self.exp_avg is None:
             self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
         g = self.gflat if g is None else g
-        L.check(L.lib.cvae_adam_step(self.n_params, _ptr(self.flat), _ptr(g), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
-                                     _ptr(self.step), lr, betas[0], betas[1], eps, grad_scale, L.stream_ptr()))
+        hi = self.n_params if hi is None else hi
+        L.check(L.lib.cvae_adam_update(hi - lo, _ptr(self.flat[lo:hi]), _ptr(g[lo:hi]), _ptr(self.exp_avg[lo:hi]), _ptr(self.exp_avg_sq[lo:hi]),
+                                       _ptr(self.step), lr, betas[0], betas[1], eps, grad_scale, int(tick), L.stream_ptr()))
+
+    def first_block_end(self):
+        """Flat offset behind encoder conv 0 and its BatchNorm: the last gradient of the backward pass to arrive (a multiple
+        of 4 floats, so both sides of the split stay 16-byte aligned)."""
+        return self.offsets[f"encoder.model.{ENC_CONV_IDX[1]}.weight"][0]
 
     @_nvtx("critic")
     def critic(self, x, weights, out=None):

@@ -267,6 +267,10 @@ int cvae_loss_bwd(int batch, const float* recon, const float* x, const float* mu
  * ---------------------------------------------------------------------------------------------- */
 int cvae_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                    int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* The same update for a RANGE of the flat buffers (the four pointers offset alike, 16-byte aligned); `tick` != 0 advances the
+ * device step counter afterwards.  One optimizer step may be applied range by range: tick only with the last one. */
+int cvae_adam_update(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t* step,
+                     float lr, float beta1, float beta2, float eps, float grad_scale, int tick, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Data-parallel training (the reference is single-GPU): NCCL all-reduce of the flat

@@ -11,12 +11,12 @@ from test_conv_gemm import _native, _rand, nhwc_bf16, rb
 pytestmark = pytest.mark.gpu
 
 
-def run_wgrad(L, kind, B, H, W, cout, cin, x, dy, dy2=None, splits=0):
+def run_wgrad(L, kind, B, H, W, cout, cin, x, dy, dy2=None, splits=0, bias=True):
     d = L.WgradDesc(kind=kind, batch=B, height=H, width=W, cout=cout, cin=cin, splits=splits,
                     x=x.data_ptr(), dy=dy.data_ptr(), dy2=dy2.data_ptr() if dy2 is not None else None)
     dw = torch.full((cout, cin, 5, 5), float("nan"), device="cuda")
     db = torch.full((cout,), float("nan"), device="cuda")
-    d.dw, d.dbias = dw.data_ptr(), db.data_ptr()
+    d.dw, d.dbias = dw.data_ptr(), (db.data_ptr() if bias else None)
     # the split-K partials live in the workspace: poison it (a partial the fold reads but no CTA wrote shows up as NaN) and tell
     # the library its size (a call that would write past it fails instead)
     need = int(L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d)))
@@ -68,6 +68,20 @@ def test_wgrad_encoder_conv0_frames(B):
     ref_w = torch.nn.grad.conv2d_weight(rb(x).double(), (32, 3, 5, 5), dy.double(), padding=2).float()
     dw, db = run_wgrad(L, L.WGRAD_SHIFT_FRAMES, B, 64, 64, 32, 3, x.cuda(), nhwc_bf16(dy))
     _check(dw, db, ref_w, dy.double().sum((0, 2, 3)).float())
+
+
+@pytest.mark.parametrize("B,splits", [(1, 0), (3, 0), (19, 0), (40, 5), (5, 1)])
+def test_wgrad_encoder_conv0_frames_without_bias(B, splits):
+    """No bias gradient (the conv sits in front of BatchNorm: what the training step asks for) takes the operand-stacked TMA
+    variant (launch_wgrad_frames): dY rows as A with four row-shifted blocks, the frames as one plane filled by the epilogue
+    warps; several chunks per CTA, chunks that run past the image and the batch, forced split counts."""
+    L = _native()
+    x = torch.rand(B, 3, 64, 64, generator=torch.Generator().manual_seed(135))
+    dy = rb(_rand((B, 32, 64, 64), 136))
+    ref_w = torch.nn.grad.conv2d_weight(rb(x).double(), (32, 3, 5, 5), dy.double(), padding=2).float()
+    dw, _ = run_wgrad(L, L.WGRAD_SHIFT_FRAMES, B, 64, 64, 32, 3, x.cuda(), nhwc_bf16(dy), splits=splits, bias=False)
+    sw = ref_w.abs().max().item()
+    np.testing.assert_allclose(dw.numpy(), ref_w.numpy(), rtol=1e-4, atol=2e-5 * sw)
 
 
 @pytest.mark.parametrize("B", [1, 3])

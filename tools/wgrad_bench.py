@@ -31,7 +31,8 @@ for name, kind, H, cin, cout in LAYERS:
     dw = torch.empty(cout, cin, 5, 5, device=dev); db = torch.empty(cout, device=dev)
     d = L.WgradDesc(kind=kind, batch=B, height=H, width=H, cout=cout, cin=cin, splits=int(os.environ.get("CVAE_SPLITS", "0")),
                     x=x.data_ptr(), dy=dy.data_ptr(), dy2=dy2.data_ptr() if dy2 is not None else None, dw=dw.data_ptr(),
-                    dbias=db.data_ptr(), workspace=ws.data_ptr())
+                    dbias=None if name.startswith("E") else db.data_ptr(),      # (encoder convs sit in front of BatchNorm: no bias gradient, as in the engine)
+                    workspace=ws.data_ptr())
     assert L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d)) <= ws.numel(), L.lib.cvae_conv_wgrad_workspace_bytes(ctypes.byref(d))
     L.check(L.lib.cvae_conv_wgrad(ctypes.byref(d), L.stream_ptr()))
     torch.cuda.synchronize()
