@@ -493,7 +493,8 @@ extern "C" int cvae_bn_fwd(int batch, int height, int width, int channels, int a
     const long long items = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
     BnFusedArgs f{(double)batch * height * width, training, stats, gamma, beta, conv_bias, running_mean, running_var,
                   (long long*)num_batches_tracked, momentum, eps, scale_shift};
-    cvae::launch(bn_fused_fwd_kernel, grid_for(items, 256), 256, 0, (cudaStream_t)stream, batch, height, width, channels, act, (const uint4*)conv_out, f,
+    static const int fwd_per_sm = getenv("CVAE_BN_FWD_BLOCKS_PER_SM") ? atoi(getenv("CVAE_BN_FWD_BLOCKS_PER_SM")) : 8;      // (experiments)
+    cvae::launch(bn_fused_fwd_kernel, grid_for(items, 256, fwd_per_sm), 256, 0, (cudaStream_t)stream, batch, height, width, channels, act, (const uint4*)conv_out, f,
                                                                                (uint4*)out, (uint4*)xhat_max, (uint16_t*)argmax);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
@@ -515,10 +516,21 @@ extern "C" int cvae_bn_pool_act_bwd(int batch, int height, int width, int channe
     long long blocks = (npix + lanes - 1) / lanes;
     const long long cap = (long long)sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    cvae::launch(bn_pool_act_bwd_kernel<0>, (int)blocks, threads, threads * 16 * sizeof(float), stream, 
+    // The reduction pass ends with 2 C double atomics per block on the same 2 C addresses, and same-address atomics
+    // serialise in L2: with 4 blocks per SM the small layers spent more time there than loading (8x8x256: 29 -> 25 us for
+    // the pair of passes at one block per SM).  One block per SM is also the best choice for the step as a whole on the
+    // large layers (1.358 -> 1.347 ms, profiles/r02_bn_bwd_pass0_grid.log: the pass shares the machine with the weight
+    // gradients of the side stream).  CVAE_BN_P0_BLOCKS_PER_SM overrides.
+    static const int p0_per_sm = getenv("CVAE_BN_P0_BLOCKS_PER_SM") && atoi(getenv("CVAE_BN_P0_BLOCKS_PER_SM")) > 0
+                                     ? atoi(getenv("CVAE_BN_P0_BLOCKS_PER_SM")) : 1;
+    long long blocks0 = (npix + lanes - 1) / lanes;
+    if (blocks0 > (long long)sm_count() * p0_per_sm) blocks0 = (long long)sm_count() * p0_per_sm;
+    cvae::launch(bn_pool_act_bwd_kernel<0>, (int)blocks0, threads, threads * 16 * sizeof(float), stream, 
         batch, height, width, channels, act, (const uint4*)conv_out, (const uint4*)act_out, (const uint4*)d_act,
         (const uint4*)xhat_max, (const uint16_t*)argmax, scale_shift, gamma, sums, nullptr, nullptr, nullptr);
     CVAE_LAUNCH_CHECK();
+    static const int p1_per_sm = getenv("CVAE_BN_P1_BLOCKS_PER_SM") ? atoi(getenv("CVAE_BN_P1_BLOCKS_PER_SM")) : 4;        // (experiments)
+    if (blocks > (long long)sm_count() * p1_per_sm) blocks = (long long)sm_count() * p1_per_sm;
     cvae::launch(bn_pool_act_bwd_kernel<1>, (int)blocks, threads, 0, stream, 
         batch, height, width, channels, act, (const uint4*)conv_out, (const uint4*)act_out, (const uint4*)d_act,
         (const uint4*)xhat_max, (const uint16_t*)argmax, scale_shift, gamma, sums, (uint4*)d_conv, dgamma, dbeta);

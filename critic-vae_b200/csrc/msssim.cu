@@ -150,6 +150,7 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
         for (int l = 0; l < 5; ++l) gcoef[l] = coef[l];
     }
 
+    double cta_tot = 0.0;      // forward, threads 0..9: this CTA's share of the ten level sums (one atomic per CTA, not per plane)
     for (int plane = blockIdx.x; plane < planes; plane += gridDim.x) {
         const float* ra = recon + (size_t)plane * 4096;
         const float* xb = x + (size_t)plane * 4096;
@@ -234,7 +235,7 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
                 const int w1 = l == 0 ? kMsThreads / 32 : (l == 1 ? 8 : (l == 2 ? 12 : (l == 3 ? 14 : 15)));
                 float tot = 0.f;
                 for (int i = w0; i < w1; ++i) tot += wsum[l > 0][which][i];
-                atomicAdd(sums + which * 5 + l, (double)tot);
+                cta_tot += (double)tot;
             }
         } else {
             __syncthreads();
@@ -271,6 +272,7 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
             }
         }
     }
+    if (!BWD && threadIdx.x < 10) atomicAdd(sums + (threadIdx.x / 5) * 5 + threadIdx.x % 5, cta_tot);
 }
 #undef CVAE_MS_FOR_TASKS
 
