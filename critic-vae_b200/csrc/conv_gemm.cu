@@ -200,28 +200,46 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, uint32_t tmem_t
     }
 }
 
+// The four epilogue warps combine their sums in shared memory (`comb`: the per-warp transposition scratch, [4 warps][32 * 17]
+// floats, free between tiles; a warp parks 2 N <= 256 sums in its own region) and warp 0 alone adds them to the
+// global statistics: same-address double atomics serialise in L2 (~20 cycles each), and all CTAs flush at the same moment at
+// the end of the kernel -- 148 per address instead of 592.  Every epilogue warp calls this at the same items (named barrier 2).
 template <int EPI, int N>
-__device__ __forceinline__ void flush_stats(const ConvArgs& a, int nb, int lane, float* s1, float* s2) {
-    if constexpr (EPI == CVAE_EPI_STATS && N == 32) {      // thread-private per-channel sums (see epilogue_tile)
-        float m1 = 0.f, m2 = 0.f;
+__device__ __forceinline__ void flush_stats(const ConvArgs& a, int nb, int warp, int lane, float* s1, float* s2, float* comb) {
+    if constexpr (EPI == CVAE_EPI_STATS) {
+        constexpr int kStride = 32 * 17;
+        static_assert(2 * N <= kStride, "statistics do not fit the per-warp scratch");
+        float* mine = comb + warp * kStride;
+        if constexpr (N == 32) {      // thread-private per-channel sums (see epilogue_tile)
+            float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float t1 = warp_sum(s1[c]), t2 = warp_sum(s2[c]);
-            if (lane == c) { m1 = t1; m2 = t2; }
-            s1[c] = s2[c] = 0.f;
+            for (int c = 0; c < 32; ++c) {
+                const float t1 = warp_sum(s1[c]), t2 = warp_sum(s2[c]);
+                if (lane == c) { m1 = t1; m2 = t2; }
+                s1[c] = s2[c] = 0.f;
+            }
+            mine[lane] = m1;
+            mine[N + lane] = m2;
+        } else {
+            if (lane < 16) {
+#pragma unroll
+                for (int g = 0; g < N / 16; ++g) {
+                    mine[g * 16 + lane] = s1[g];
+                    mine[N + g * 16 + lane] = s2[g];
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < N / 16; ++g) s1[g] = s2[g] = 0.f;
         }
-        atomicAdd(a.stats + nb * N + lane, (double)m1);
-        atomicAdd(a.stats + a.c_total + nb * N + lane, (double)m2);
-    } else if constexpr (EPI == CVAE_EPI_STATS) {
-        if (lane < 16) {
-#pragma unroll
-            for (int g = 0; g < N / 16; ++g) {
-                atomicAdd(a.stats + nb * N + g * 16 + lane, (double)s1[g]);
-                atomicAdd(a.stats + a.c_total + nb * N + g * 16 + lane, (double)s2[g]);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 0) {
+            for (int c = lane; c < 2 * N; c += 32) {
+                const float t = (comb[c] + comb[kStride + c]) + (comb[2 * kStride + c] + comb[3 * kStride + c]);
+                const int which = c / N, ch = c - which * N;
+                atomicAdd(a.stats + which * a.c_total + nb * N + ch, (double)t);
             }
         }
-#pragma unroll
-        for (int g = 0; g < N / 16; ++g) s1[g] = s2[g] = 0.f;
+        asm volatile("bar.sync 2, 128;" ::: "memory");      // comb may be rewritten by the next flush
     }
 }
 
@@ -437,7 +455,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvAr
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int nb = item / a.num_chunks, chunk = item - nb * a.num_chunks;
             if (nb != cur_nb) {
-                if (cur_nb >= 0) flush_stats<EPI, N>(a, cur_nb, lane, s1, s2);
+                if (cur_nb >= 0) flush_stats<EPI, N>(a, cur_nb, warp, lane, s1, s2, stat_scratch);
                 cur_nb = nb;
             }
             const uint32_t ab = it & 1u;
@@ -454,7 +472,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvAr
             t_epi += clock64() - te;
         }
         if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 8 + 7] = t_epi;
-        if (cur_nb >= 0) flush_stats<EPI, N>(a, cur_nb, lane, s1, s2);
+        if (cur_nb >= 0) flush_stats<EPI, N>(a, cur_nb, warp, lane, s1, s2, stat_scratch);
     } else if (warp == kPipeThreads / 32 - 1) {
         // ================================ MMA issuer (highest warp id: the scheduler favours it) ==============================================
         if (elect_one()) {

@@ -437,11 +437,22 @@ conv_wa_kernel(const WaArgs a, const __grid_constant__ CUtensorMap map0, const _
         if (a.dbg && tid == 0) { a.dbg[(size_t)blockIdx.x * 16 + 6] = (unsigned long long)t_epi; a.dbg[(size_t)blockIdx.x * 16 + 7] = (unsigned long long)t_red; }
         if (a.dbg && lane == 0) atomicMax(a.dbg + (size_t)blockIdx.x * 16 + 12, wa_now_ns());    // last epilogue warp done
         if constexpr (EPI == CVAE_EPI_STATS) {
-            if (J == 1 || lane < 32 / J) {
+            // warps w and w + 4 hold the sums of the same channels (the two column halves): combine them in shared memory, one
+            // set of double atomics per CTA (same-address atomics serialise in L2 and every CTA flushes at the same moment)
+            // (the pixel ring at the start of the dynamic shared memory is dead by now: every tile of this CTA has been
+            // through its MMAs and its epilogue; static shared memory has no room left beside the largest stage plans)
+            float (*stat_comb)[2][2][32] = reinterpret_cast<float (*)[2][2][32]>(smem);      // [warp & 3][m block parity][sum | sum of squares][lane]
+            asm volatile("bar.sync 2, 256;" ::: "memory");      // all eight epilogue warps are past their last tile
+            if (warp >= 4) {
+#pragma unroll
+                for (int p = 0; p < 2; ++p) { stat_comb[warp & 3][p][0][lane] = s1[p]; stat_comb[warp & 3][p][1][lane] = s2[p]; }
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (warp < 4 && (J == 1 || lane < 32 / J)) {
                 for (int mb = 0; mb < a.m_blocks; ++mb) {
                     const int co = mb * (128 / J) + (warp & 3) * (32 / J) + lane;
-                    atomicAdd(a.stats + co, (double)s1[mb & 1]);
-                    atomicAdd(a.stats + a.c_total + co, (double)s2[mb & 1]);
+                    atomicAdd(a.stats + co, (double)(s1[mb & 1] + stat_comb[warp][mb & 1][0][lane]));
+                    atomicAdd(a.stats + a.c_total + co, (double)(s2[mb & 1] + stat_comb[warp][mb & 1][1][lane]));
                 }
             }
         }
