@@ -1,6 +1,6 @@
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-run() { timeout 600 python bench.py --steps 300 --warmup 10 --no-secondary 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])"; }
-echo "bench"; run; run
-timeout 300 python tools/conv_bench.py 2>&1 | grep "E0f\|E1f\|E2f\|E3f"
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 200 --warmup 10 > gpurun_out/r02_bench_8gpu.json 2> gpurun_out/r02_bench_8gpu.err; tail -2 gpurun_out/r02_bench_8gpu.err | cut -c1-300
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02_bench_8gpu.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','n_gpus','scaling','clocks')}); print('e2e', d['e2e']['value']); print('cfg4', d.get('cfg4'))
+PY
