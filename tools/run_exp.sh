@@ -1,6 +1,3 @@
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 200 --warmup 10 > gpurun_out/r02_bench_8gpu.json 2> gpurun_out/r02_bench_8gpu.err; tail -2 gpurun_out/r02_bench_8gpu.err | cut -c1-300
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r02_bench_8gpu.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','n_gpus','scaling','clocks')}); print('e2e', d['e2e']['value']); print('cfg4', d.get('cfg4'))
-PY
+timeout 300 python tools/profile_step.py 256 3 2>&1 | tail -1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_step_launches_b256_final.csv python tools/profile_step.py 256 3 > gpurun_out/ncu_list.log 2>&1; tail -1 gpurun_out/ncu_list.log
+python tools/launch_table.py gpurun_out/r02_step_launches_b256_final.csv > gpurun_out/r02_step_launches_b256_final.md 2>&1; tail -3 gpurun_out/r02_step_launches_b256_final.md
