@@ -396,14 +396,17 @@ __device__ __forceinline__ void mma_role_ks(const ConvArgs& a, PipeBars& bars, u
 // --------------------------------------------------------------------------------------------
 // pipelined kernel
 // --------------------------------------------------------------------------------------------
-static constexpr int kPipeThreads = 320;
-static constexpr int kProducerThreads = 128;  // warps 6-9
+// Warps 0-3 epilogue, then the plane producers, then the weight producer and the MMA issuer (the last two warps).
+// Encoder conv 0's producers convert fp32 frames themselves and were its limiter: that loader gets eight producer warps.
+template <int LOADER> constexpr int pipe_threads() { return LOADER == CVAE_LOAD_NCHW3 ? 448 : 320; }
+template <int LOADER> constexpr int pipe_producers() { return pipe_threads<LOADER>() - 192; }
 static size_t kStageBytesMax = getenv("CVAE_STAGE_KB") ? (size_t)atoi(getenv("CVAE_STAGE_KB")) * 1024 : 0;   // 0: automatic
 static int kMaxGroupPlanes = getenv("CVAE_GROUP_PLANES") ? atoi(getenv("CVAE_GROUP_PLANES")) : 0;         // 0: automatic
 static constexpr size_t kDynSmemMax = 216 * 1024;  // 227 KB per CTA minus static shared memory (barriers, statistics scratch)
 
 template <int LOADER, int EPI, int N, int KW>
-__global__ void __launch_bounds__(kPipeThreads, 1) conv_pipe_kernel(const ConvArgs a) {
+__global__ void __launch_bounds__(pipe_threads<LOADER>(), 1) conv_pipe_kernel(const ConvArgs a) {
+    constexpr int kPipeThreads = pipe_threads<LOADER>(), kProducerThreads = pipe_producers<LOADER>();
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ PipeBars bars;
     uint64_t* const w_full = bars.w_full; uint64_t* const w_empty = bars.w_empty;
@@ -598,7 +601,7 @@ static int launch_pipe(const ConvArgs& a, size_t smem, cudaStream_t stream) {
         fprintf(stderr, "conv_pipe<L%d,E%d,N%d> B=%d %dx%d planes=%dx%d ksteps=%d kpg=%d ksps=%d stages=%d%s tm=%d chunks=%d "
                         "nblk=%d smem=%zu grid=%d\n", LOADER, EPI, N, a.B, a.H, a.W, a.planes, a.ncg, a.ksteps, a.kpg, a.ksps,
                 a.nstages, a.resident ? "(resident)" : "", a.tm, a.num_chunks, a.n_blocks, smem, gx);
-    cvae::launch(kern, gx, kPipeThreads, smem, stream, a);
+    cvae::launch(kern, gx, pipe_threads<LOADER>(), smem, stream, a);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }
