@@ -138,6 +138,7 @@ class VAEEngine:
         self.side_stream = None
         self.fold_stream = None     # third stream: split-K folds beside the next weight-gradient GEMM
         self.early_event = None     # optional torch.cuda.Event(external=True) recorded when the early gradient bucket is final
+        self.mid_event = None       # the same for the middle bucket (encoder convs 2 and 3): mid_bucket_offset() .. early_bucket_offset()
         # the three layers around the latent as one launch per direction in the training step (CVAE_NO_FUSED_BOTTLENECK=1: six launches)
         self.fused_bottleneck = os.environ.get("CVAE_NO_FUSED_BOTTLENECK") is None
         self.early_adam = None      # dict(lr=, grad_scale=): update all parameters but the first conv block inside backward()
@@ -436,6 +437,11 @@ class VAEEngine:
         decoder and the heads, long before the encoder's own gradients -- the data-parallel step all-reduces it beside them."""
         return self.offsets["encoder.fc_mu.weight"][0]
 
+    def mid_bucket_offset(self):
+        """Inside the encoder part, convs 2 and 3 (with their BatchNorm) hold 97 % of the floats and are final two layers
+        before the end of the backward pass: [mid_bucket_offset(), early_bucket_offset()) is a bucket of its own."""
+        return self.offsets[f"encoder.model.{ENC_CONV_IDX[2]}.weight"][0]
+
     @_nvtx("backward")
     def backward(self, x, eps, ws, d_recon, d_mu, d_lv, g=None, kld_grad_scale=0.0, stage="all"):
         """Gradients of every parameter into the flat buffer `g` (default self.gflat), given the
@@ -521,6 +527,12 @@ class VAEEngine:
                 self._wgrad(g, cname, kind=L.WGRAD_SHIFT_FRAMES, batch=B, height=64, width=64, cout=32, cin=3, x=x, dy=ws.g_c[0])
             else:
                 self._wgrad(g, cname, kind=L.WGRAD_5X5, batch=B, height=h, width=h, cout=co, cin=ci, x=ws.a[i - 1], dy=ws.g_c[i])
+                if i == 2 and self.mid_event is not None and self.side_stream is not None and self.profile is None:
+                    # encoder convs 3 and 2 (+ their BatchNorm) are final once the side and fold streams reach this point:
+                    # 97 % of the encoder's gradient floats, ready while convs 1 and 0 are still being walked
+                    if self._fold_used:
+                        self.side_stream.wait_stream(self.fold_stream)
+                    self.mid_event.record(self.side_stream)
                 self._conv(f"E{i}g", batch=B, height=h, width=h, ksize=5, src_channels=co, n_total=ci, loader=L.LOAD_NHWC,
                            epilogue=L.EPI_PLAIN, ktab=L.KTAB_GENERIC, src=ws.g_c[i], wpack=self.packed[f"E{i}g"], out=ws.g_a[i - 1])
 

@@ -69,6 +69,10 @@ class TrainStep:
         if self.overlap:
             self.comm_stream = torch.cuda.Stream()
             self.early_event = torch.cuda.Event(external=True)
+            # CVAE_DP_BUCKETS=3: encoder convs 3 and 2 as a bucket of their own (second external event).  Measured slower than
+            # two buckets at 2 and at 8 GPUs (1.427 vs 1.417 ms, 1.459 vs 1.453 ms): another NCCL kernel in the middle of the
+            # backward pass costs more than the smaller last all-reduce saves.  Off by default.
+            self.mid_event = torch.cuda.Event(external=True) if os.environ.get("CVAE_DP_BUCKETS", "2") == "3" else None
         # CVAE_COMM=native: the all-reduce goes through libcvae's own NCCL communicator (cvae_comm_*, csrc/comm.cu), the path a
         # non-Python host would use; torch.distributed then only carries the 128 rendezvous bytes.  Default: torch.distributed.
         self.native_comm = self.world > 1 and os.environ.get("CVAE_COMM") == "native"
@@ -114,6 +118,7 @@ class TrainStep:
         eng.loss_forward(ws.recon, self.x, ws.ml, ws, fused_kld=not fused)
         eng.loss_backward(ws.recon, self.x, ws.ml, ws, fused_kld=True)
         eng.early_event = self.early_event if self.overlap else None      # (the engine is shared between TrainSteps)
+        eng.mid_event = self.mid_event if self.overlap else None
         # CVAE_EARLY_ADAM=1 (one GPU): Adam for everything but the first conv block runs beside that block's weight gradient,
         # the last kernel of the backward pass.  Measured: 1.397 ms against 1.388 ms with one Adam launch behind it (the
         # update competes with the GEMM it was meant to hide behind), so it is off by default.
@@ -121,6 +126,7 @@ class TrainStep:
         eng.early_adam = dict(lr=self.lr, grad_scale=1.0) if self._adam_split else None
         eng.backward(self.x, self.eps, ws, ws.d_recon, None, None, kld_grad_scale=KLD_WEIGHT / self.B, stage=stage)
         eng.early_event = None
+        eng.mid_event = None
         eng.early_adam = None
 
     def _front_encoder(self):
@@ -133,21 +139,28 @@ class TrainStep:
             self.eng.adam_step(self.lr, grad_scale=1.0 / self.world)
 
     def _buckets(self):
-        """(early, late) views of the flat gradient: see VAEEngine.early_bucket_offset."""
+        """(early, mid, late) views of the flat gradient in the order they become final: heads + decoder, encoder convs 3 and 2,
+        encoder convs 1 and 0 (VAEEngine.early_bucket_offset / mid_bucket_offset); mid is None with two buckets."""
         off = self.eng.early_bucket_offset()
-        return self.eng.gflat[off:], self.eng.gflat[:off]
+        if self.overlap and self.mid_event is not None:
+            mid = self.eng.mid_bucket_offset()
+            return self.eng.gflat[off:], self.eng.gflat[mid:off], self.eng.gflat[:mid]
+        return self.eng.gflat[off:], None, self.eng.gflat[:off]
 
     def _allreduce(self):
         """Sum the flat gradient over the ranks, after _front has been launched on the current stream: the early bucket
         on the communication stream as soon as the event inside the backward pass fires (beside the encoder's backward
         pass), the late bucket behind the whole pass; the current stream then waits for both."""
-        early, late = self._buckets()
+        early, mid, late = self._buckets()
         if self.native_comm:
             reduce_ = lambda t: L.check(L.lib.cvae_comm_allreduce_sum(t.data_ptr(), t.numel(), L.stream_ptr()))
             if self.overlap:
                 with torch.cuda.stream(self.comm_stream):
                     self.comm_stream.wait_event(self.early_event)
                     reduce_(early)
+                    if mid is not None:
+                        self.comm_stream.wait_event(self.mid_event)
+                        reduce_(mid)
                     done = torch.cuda.Event()
                     done.record()
                 reduce_(late)
@@ -155,11 +168,16 @@ class TrainStep:
             else:
                 reduce_(self.eng.gflat)
         elif self.overlap:
+            works = []
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(self.early_event)
-                w1 = torch.distributed.all_reduce(early, group=self.pg, async_op=True)
-            w2 = torch.distributed.all_reduce(late, group=self.pg, async_op=True)
-            w1.wait(); w2.wait()
+                works.append(torch.distributed.all_reduce(early, group=self.pg, async_op=True))
+                if mid is not None:
+                    self.comm_stream.wait_event(self.mid_event)
+                    works.append(torch.distributed.all_reduce(mid, group=self.pg, async_op=True))
+            works.append(torch.distributed.all_reduce(late, group=self.pg, async_op=True))
+            for w in works:
+                w.wait()
         else:
             torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
 
