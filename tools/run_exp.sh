@@ -1,3 +1,8 @@
-for b in 3 2 3 2; do CVAE_DP_BUCKETS=$b timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 300 --warmup 10 --no-secondary 2>/dev/null | python -c "
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 --no-secondary 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('buckets=$b', d['value'], d['ms_per_step'])"; done
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=2', d['value'], d['ms_per_step'])"
+timeout 300 python bench.py --steps 200 --warmup 10 --no-secondary 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=1', d['value'], d['ms_per_step'], d['e2e']['value'])"
