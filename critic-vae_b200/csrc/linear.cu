@@ -565,7 +565,8 @@ static int max_clusters_of(K kern, int threads, size_t smem) {
 }
 // rows per cluster: 16 unless that needs more clusters than fit at once and 20 does not
 static int bottleneck_rows(int batch, int max_clusters) {
-    if (const char* e = getenv("CVAE_BOTTLENECK_ROWS")) return atoi(e) == 20 ? 20 : 16;      // (experiments)
+    static const int forced = getenv("CVAE_BOTTLENECK_ROWS") ? atoi(getenv("CVAE_BOTTLENECK_ROWS")) : 0;      // (experiments; read once)
+    if (forced) return forced == 20 ? 20 : 16;
     if (max_clusters <= 0) return 16;
     const int c16 = (batch + 15) / 16, c20 = (batch + 19) / 20;
     return (c16 > max_clusters && c20 <= max_clusters) ? 20 : 16;
@@ -608,11 +609,14 @@ extern "C" int cvae_bottleneck_fwd(int batch, const void* act, const float* wfc,
                  "bottleneck_fwd: bad argument");
     int* fault = fault_flag();
     CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "bottleneck_fwd: fault flag unavailable");
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
+    static int cap_of_device[64] = {0};      // cluster capacity per device (0: not asked yet, -1: unknown)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (cap_of_device[dev] == 0) {
         CVAE_OPT_IN_SMEM(bottleneck_fwd_kernel<16>, bn_fwd_smem<16>());
-        max_clusters = max_clusters_of(bottleneck_fwd_kernel<16>, 256, bn_fwd_smem<16>());
+        cap_of_device[dev] = max_clusters_of(bottleneck_fwd_kernel<16>, 256, bn_fwd_smem<16>());
     }
+    const int max_clusters = cap_of_device[dev];
     if (bottleneck_rows(batch, max_clusters) == 20)
         return launch_bottleneck_fwd<20>(batch, act, wfc, bias_mu, bias_var, eps, pred, wdec, mu_logvar, z_pred, dec_in, fault, stream);
     return launch_bottleneck_fwd<16>(batch, act, wfc, bias_mu, bias_var, eps, pred, wdec, mu_logvar, z_pred, dec_in, fault, stream);
@@ -637,11 +641,14 @@ extern "C" int cvae_bottleneck_bwd(int batch, const void* d_dec_in, const float*
     CVAE_REQUIRE(batch > 0 && d_dec_in && wdec && mu_logvar && eps && wfc && d_mu_logvar && d_act, CVAE_EINVAL, "bottleneck_bwd: bad argument");
     int* fault = fault_flag();
     CVAE_REQUIRE(fault != nullptr, CVAE_ECUDA, "bottleneck_bwd: fault flag unavailable");
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
+    static int cap_of_device[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (cap_of_device[dev] == 0) {
         CVAE_OPT_IN_SMEM(bottleneck_bwd_kernel<16>, bn_bwd_smem<16>());
-        max_clusters = max_clusters_of(bottleneck_bwd_kernel<16>, 256, bn_bwd_smem<16>());
+        cap_of_device[dev] = max_clusters_of(bottleneck_bwd_kernel<16>, 256, bn_bwd_smem<16>());
     }
+    const int max_clusters = cap_of_device[dev];
     if (bottleneck_rows(batch, max_clusters) == 20)
         return launch_bottleneck_bwd<20>(batch, d_dec_in, wdec, mu_logvar, eps, kld_grad_scale, wfc, d_z_pred, d_mu_logvar, d_act, fault, stream);
     return launch_bottleneck_bwd<16>(batch, d_dec_in, wdec, mu_logvar, eps, kld_grad_scale, wfc, d_z_pred, d_mu_logvar, d_act, fault, stream);

@@ -36,6 +36,11 @@ def test_argument_validation_without_gpu():
     assert L.lib.cvae_adam_step(0, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1.0, None) == -1
     assert L.lib.cvae_mask_iou(-1, None, None, 1.0, 1.0, 50, 0, None, None, None, None, None, None) == -1
     assert L.lib.cvae_conv_ksteps(5, 64, L.KTAB_GENERIC) == 100 and L.lib.cvae_conv_ksteps(5, 8, L.KTAB_PAIR8) == 13
+    # entry points added in round 2 refuse null tensors before they touch the device
+    assert L.lib.cvae_adam_update(8, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1.0, 0, None) == -1
+    assert L.lib.cvae_bottleneck_fwd(4, None, None, None, None, None, None, None, None, None, None, None) == -1 and b"bottleneck_fwd" in L.lib.cvae_last_error()
+    assert L.lib.cvae_bottleneck_bwd(4, None, None, None, None, 0.0, None, None, None, None, None) == -1 and b"bottleneck_bwd" in L.lib.cvae_last_error()
+    assert L.lib.cvae_bn_fwd(0, 8, 8, 32, 0, 1, None, None, None, None, None, None, None, None, 0.1, 1e-5, None, None, None, None, None) == -1
     # the communicator entry points (csrc/comm.cu): nothing exists before cvae_comm_init, and bad ranks are refused
     assert L.lib.cvae_comm_world() == 0
     assert L.lib.cvae_comm_allreduce_sum(None, 4, None) == -1 and b"no communicator" in L.lib.cvae_last_error()
