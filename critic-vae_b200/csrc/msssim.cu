@@ -129,6 +129,23 @@ __device__ __forceinline__ void vpass(int S, int t, const Window& w, const float
         else if (out_ == 1) { constexpr int OUT = 1; const int lvl = lvl_, S = 64 >> lvl_, t = t_; __VA_ARGS__ } \
     }
 
+// The scalar part of the loss from the ten batch-global level sums (vae_nets.py:224-246): returns P = prod_l<4 (cs_l^w_l *
+// ssim_4^w_4) (recon loss = 1 - P) and writes the chain-rule coefficients dL/d(map pixel): coef[0..3] for the cs maps of
+// levels 0..3, coef[4] for the ssim map of level 4.  Shared by loss_finalize_kernel and by the backward kernel when it is
+// given the sums instead of the coefficients (so that loss_finalize can run beside it).
+__device__ __forceinline__ float ms_chain_coefficients(const double* __restrict__ sums, int B, float* coef) {
+    const float wts[5] = {0.0448f, 0.2856f, 0.3001f, 0.2363f, 0.1333f};
+    float cs[5], ss4, P = 1.f;
+    for (int l = 0; l < 5; ++l) cs[l] = (float)(sums[l] / ((double)B * 3 * lvl_size(l) * lvl_size(l)));
+    ss4 = (float)(sums[9] / ((double)B * 3 * 16));
+    const float p4 = powf(ss4, wts[4]);
+    for (int l = 0; l < 4; ++l) P *= powf(cs[l], wts[l]) * p4;   // torch.prod(pow1[:-1] * pow2[-1])
+    // L = 1 - P;  dL/dcs_l = -P w_l / cs_l;  dL/dss4 = -P 4 w_4 / ss4;  per-pixel: / N_l
+    for (int l = 0; l < 4; ++l) coef[l] = (-P * wts[l] / cs[l]) / ((float)B * 3.f * lvl_size(l) * lvl_size(l));
+    coef[4] = (-P * 4.f * wts[4] / ss4) / ((float)B * 3.f * 16.f);
+    return P;
+}
+
 // coef layout (floats): [0..3] dL/d(cs_map pixel) for levels 0..3, [4] dL/d(ssim_map pixel) level 4
 template <bool BWD>
 __global__ void __launch_bounds__(kMsThreads, 1)
@@ -146,8 +163,12 @@ msssim_kernel(int planes, const float* __restrict__ recon, const float* __restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float gcoef[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (BWD) {
+        if (coef != nullptr) {
 #pragma unroll
-        for (int l = 0; l < 5; ++l) gcoef[l] = coef[l];
+            for (int l = 0; l < 5; ++l) gcoef[l] = coef[l];
+        } else {
+            ms_chain_coefficients(sums, planes / 3, gcoef);      // (every thread for itself: five powf, no barrier)
+        }
     }
 
     double cta_tot = 0.0;      // forward, threads 0..9: this CTA's share of the ten level sums (one atomic per CTA, not per plane)
@@ -300,20 +321,13 @@ __global__ void loss_finalize_kernel(int B, const float* __restrict__ ml, const 
         double tot = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
         const float kld = (float)(-0.5 * tot / B) * kld_weight;
-        const float wts[5] = {0.0448f, 0.2856f, 0.3001f, 0.2363f, 0.1333f};
-        float cs[5], ss4, P = 1.f;
-        for (int l = 0; l < 5; ++l) cs[l] = (float)(sums[l] / ((double)B * 3 * lvl_size(l) * lvl_size(l)));
-        ss4 = (float)(sums[9] / ((double)B * 3 * 16));
-        const float p4 = powf(ss4, wts[4]);
-        for (int l = 0; l < 4; ++l) P *= powf(cs[l], wts[l]) * p4;   // torch.prod(pow1[:-1] * pow2[-1])
+        float c[5];
+        const float P = ms_chain_coefficients(sums, B, c);
         const float recon_loss = 1.f - P;
         losses[0] = recon_loss + kld;
         losses[1] = recon_loss;
         losses[2] = kld;
-        // L = 1 - P;  dL/dcs_l = -P w_l / cs_l;  dL/dss4 = -P 4 w_4 / ss4;  per-pixel: / N_l
-        for (int l = 0; l < 4; ++l)
-            coef[l] = (-P * wts[l] / cs[l]) / ((float)B * 3.f * lvl_size(l) * lvl_size(l));
-        coef[4] = (-P * 4.f * wts[4] / ss4) / ((float)B * 3.f * 16.f);
+        for (int l = 0; l < 5; ++l) coef[l] = c[l];
     }
 }
 
@@ -347,11 +361,11 @@ static int ms_grid(int planes) {
     return (planes + rounds - 1) / rounds;
 }
 
-extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar, const double* kld_partial,
-                             const float* window11, float kld_weight, double* sums, float* coef, float* losses,
-                             void* stream_) {
+// The two halves of cvae_loss_fwd as calls of their own, so that a training step can run the second one (the scalars the host
+// reads: one block) on another stream beside cvae_loss_bwd_sums, which derives its coefficients from the sums itself.
+extern "C" int cvae_loss_sums(int batch, const float* recon, const float* x, const float* window11, double* sums, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    CVAE_REQUIRE(batch > 0 && recon && x && (mu_logvar || kld_partial) && window11 && sums && coef && losses, CVAE_EINVAL, "loss_fwd: bad argument");
+    CVAE_REQUIRE(batch > 0 && recon && x && window11 && sums, CVAE_EINVAL, "loss_sums: bad argument");
     Window w;
     memcpy(w.g, window11, sizeof(w.g));
     CVAE_OPT_IN_SMEM(msssim_kernel<false>, ms_smem(false));
@@ -360,7 +374,40 @@ extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, cons
     const int grid = ms_grid(planes);
     cvae::launch(msssim_kernel<false>, grid, kMsThreads, ms_smem(false), stream, planes, recon, x, w, sums, nullptr, nullptr, nullptr);
     CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_loss_finalize(int batch, const float* mu_logvar, const double* kld_partial, const double* sums, float kld_weight,
+                                  float* coef, float* losses, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVAE_REQUIRE(batch > 0 && (mu_logvar || kld_partial) && sums && coef && losses, CVAE_EINVAL, "loss_finalize: bad argument");
     cvae::launch(loss_finalize_kernel, 1, kld_partial ? 32 : 1024, 0, stream, batch, mu_logvar, kld_partial, (batch + 63) / 64, sums, kld_weight, losses, coef);
+    CVAE_LAUNCH_CHECK();
+    return CVAE_OK;
+}
+
+extern "C" int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu_logvar, const double* kld_partial,
+                             const float* window11, float kld_weight, double* sums, float* coef, float* losses,
+                             void* stream_) {
+    CVAE_REQUIRE(batch > 0 && recon && x && (mu_logvar || kld_partial) && window11 && sums && coef && losses, CVAE_EINVAL, "loss_fwd: bad argument");
+    const int rc = cvae_loss_sums(batch, recon, x, window11, sums, stream_);
+    if (rc != CVAE_OK) return rc;
+    return cvae_loss_finalize(batch, mu_logvar, kld_partial, sums, kld_weight, coef, losses, stream_);
+}
+
+// d(recon loss)/d(recon) from the level sums cvae_loss_sums left (the coefficients cvae_loss_finalize would hand to
+// cvae_loss_bwd are recomputed in the kernel: bit-identical); the KL term's gradient is the caller's (cvae_latent_bwd /
+// cvae_bottleneck_bwd with kld_grad_scale).
+extern "C" int cvae_loss_bwd_sums(int batch, const float* recon, const float* x, const float* window11, const double* sums,
+                                  const float* grad_out, float* d_recon, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CVAE_REQUIRE(batch > 0 && recon && x && window11 && sums && d_recon, CVAE_EINVAL, "loss_bwd_sums: bad argument");
+    Window w;
+    memcpy(w.g, window11, sizeof(w.g));
+    CVAE_OPT_IN_SMEM(msssim_kernel<true>, ms_smem(true));
+    const int planes = batch * 3;
+    const int grid = ms_grid(planes);
+    cvae::launch(msssim_kernel<true>, grid, kMsThreads, ms_smem(true), stream, planes, recon, x, w, const_cast<double*>(sums), nullptr, grad_out, d_recon);
     CVAE_LAUNCH_CHECK();
     return CVAE_OK;
 }

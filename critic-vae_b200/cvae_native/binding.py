@@ -91,6 +91,9 @@ _SIGS = {
     "cvae_adam_step": ([c_i64, P, P, P, P, P, c_float, c_float, c_float, c_float, c_float, P], c_int),
     "cvae_adam_update": ([c_i64, P, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int, P], c_int),
     "cvae_critic_param_count": ([], c_int),
+    "cvae_loss_sums": ([c_int, P, P, P, P, P], c_int),
+    "cvae_loss_finalize": ([c_int, P, P, P, ctypes.c_float, P, P, P], c_int),
+    "cvae_loss_bwd_sums": ([c_int, P, P, P, P, P, P, P], c_int),
     "cvae_bottleneck_debug": ([P], c_int),
     "cvae_bottleneck_max_clusters": ([c_int, c_i64], c_int),
     "cvae_bottleneck_fwd": ([c_int] + [P] * 11, c_int),

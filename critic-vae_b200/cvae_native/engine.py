@@ -144,6 +144,7 @@ class VAEEngine:
         self.early_adam = None      # dict(lr=, grad_scale=): update all parameters but the first conv block inside backward()
         self.adam_stream = None
         self._adam_used = False
+        self._loss_on_side = False
 
     # ---- parameters ---------------------------------------------------------------------------
     def view(self, name, buf=None):
@@ -348,18 +349,35 @@ class VAEEngine:
 
     # ---- loss ---------------------------------------------------------------------------------
     @_nvtx("loss_forward")
-    def loss_forward(self, recon, x, ml, ws, kld_weight=KLD_WEIGHT, fused_kld=False):
+    def loss_forward(self, recon, x, ml, ws, kld_weight=KLD_WEIGHT, fused_kld=False, split=False):
         """`fused_kld`: ml is ws.ml of the decode() that just ran with sample=True, so the KL partial sums the latent
         kernel left in ws.kld_partial are used instead of re-reading mu / logvar (a decode() with its head; after
         bottleneck_forward there are no partials and the loss kernel reduces mu / logvar itself)."""
+        if split and self.side_stream is not None and self.profile is None:
+            # level sums on this stream; the scalars the host reads (one block: KL reduction, five powf) on the side stream,
+            # off the critical path -- loss_backward(split=True) derives its coefficients from the sums itself
+            L.check(L.lib.cvae_loss_sums(ws.B, _ptr(recon), _ptr(x), self.window, _ptr(ws.loss_sums), L.stream_ptr()))
+            ev = torch.cuda.Event()
+            ev.record()
+            self.side_stream.wait_event(ev)
+            with torch.cuda.stream(self.side_stream):
+                L.check(L.lib.cvae_loss_finalize(ws.B, _ptr(ml), _ptr(ws.kld_partial) if fused_kld else None, _ptr(ws.loss_sums), kld_weight,
+                                                 _ptr(ws.coef), _ptr(ws.losses), L.stream_ptr()))
+            self._loss_on_side = True
+            return ws.losses
         L.check(L.lib.cvae_loss_fwd(ws.B, _ptr(recon), _ptr(x), _ptr(ml), _ptr(ws.kld_partial) if fused_kld else None, self.window,
                                     kld_weight, _ptr(ws.loss_sums), _ptr(ws.coef), _ptr(ws.losses), L.stream_ptr()))
         return ws.losses
 
     @_nvtx("loss_backward")
-    def loss_backward(self, recon, x, ml, ws, grad_out=None, kld_weight=KLD_WEIGHT, fused_kld=False):
+    def loss_backward(self, recon, x, ml, ws, grad_out=None, kld_weight=KLD_WEIGHT, fused_kld=False, split=False):
         """`fused_kld`: skip the KL term's backward here; backward(..., kld_grad_scale=kld_weight / B) adds it inside the
-        latent backward kernel (only valid with grad_out None, i.e. an upstream gradient of 1)."""
+        latent backward kernel (only valid with grad_out None, i.e. an upstream gradient of 1).
+        `split` (with fused_kld, after loss_forward(split=True)): the kernel computes its coefficients from ws.loss_sums."""
+        if split and fused_kld:
+            L.check(L.lib.cvae_loss_bwd_sums(ws.B, _ptr(recon), _ptr(x), self.window, _ptr(ws.loss_sums), _ptr(grad_out), _ptr(ws.d_recon),
+                                             L.stream_ptr()))
+            return ws.d_recon, ws.d_mu, ws.d_lv
         L.check(L.lib.cvae_loss_bwd(ws.B, _ptr(recon), _ptr(x), _ptr(ml), self.window, kld_weight, _ptr(ws.coef),
                                     _ptr(grad_out), _ptr(ws.d_recon), None if fused_kld else _ptr(ws.d_mu),
                                     None if fused_kld else _ptr(ws.d_lv), L.stream_ptr()))
@@ -452,7 +470,9 @@ class VAEEngine:
         B, s = ws.B, L.stream_ptr()
         G = lambda n: self.view(n, g)
         if stage != "encoder":
-            self._side_used = self._fold_used = False
+            self._side_used = self._loss_on_side      # (a loss_finalize launched on the side stream by loss_forward(split=True))
+            self._fold_used = False
+            self._loss_on_side = False
             self._backward_decoder(x, eps, ws, d_recon, d_mu, d_lv, g, kld_grad_scale)
             if stage == "decoder":
                 self._join_leaves()

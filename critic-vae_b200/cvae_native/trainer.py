@@ -115,8 +115,11 @@ class TrainStep:
         eng.decode(self.pred, self.eps, True, ws, head=not fused)
         # the KL term rides along with the latent kernels: partial sums in the forward (separate kernels only; the loss kernel
         # reduces mu / logvar itself behind the fused bottleneck), its gradient in the backward
-        eng.loss_forward(ws.recon, self.x, ws.ml, ws, fused_kld=not fused)
-        eng.loss_backward(ws.recon, self.x, ws.ml, ws, fused_kld=True)
+        # CVAE_LOSS_SPLIT=1: loss scalars (one block) on the side stream, the backward kernel derives its coefficients from the
+        # level sums.  Measured slower (1.362 vs 1.355 ms): the fork costs more than the 8 us kernel it takes off the chain.
+        split = os.environ.get("CVAE_LOSS_SPLIT") == "1"
+        eng.loss_forward(ws.recon, self.x, ws.ml, ws, fused_kld=not fused, split=split)
+        eng.loss_backward(ws.recon, self.x, ws.ml, ws, fused_kld=True, split=split)
         eng.early_event = self.early_event if self.overlap else None      # (the engine is shared between TrainSteps)
         eng.mid_event = self.mid_event if self.overlap else None
         # CVAE_EARLY_ADAM=1 (one GPU): Adam for everything but the first conv block runs beside that block's weight gradient,

@@ -259,6 +259,13 @@ int cvae_loss_fwd(int batch, const float* recon, const float* x, const float* mu
 int cvae_loss_bwd(int batch, const float* recon, const float* x, const float* mu_logvar, const float* window11,
                   float kld_weight, const float* coef, const float* grad_out, float* d_recon, float* d_mu,
                   float* d_logvar, void* stream);
+/* cvae_loss_fwd in two calls (level sums, then the scalars + coefficients), and the reconstruction-loss gradient straight from
+ * the sums: a training step runs cvae_loss_finalize (one block) on another stream beside cvae_loss_bwd_sums.  Same results. */
+int cvae_loss_sums(int batch, const float* recon, const float* x, const float* window11, double* sums, void* stream);
+int cvae_loss_finalize(int batch, const float* mu_logvar, const double* kld_partial, const double* sums, float kld_weight,
+                       float* coef, float* losses, void* stream);
+int cvae_loss_bwd_sums(int batch, const float* recon, const float* x, const float* window11, const double* sums,
+                       const float* grad_out, float* d_recon, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Adam (torch.optim.Adam defaults, vae.py:36,58) on flat fp32 buffers; `step` is a device int64

@@ -263,6 +263,17 @@ def test_loss_forward_backward_vs_golden(golden_dir, tag, B):
     dmu, dlv = torch.zeros(B, 32, device="cuda"), torch.zeros(B, 32, device="cuda")
     L.check(L.lib.cvae_loss_bwd(B, ptr(rd), ptr(xd), ptr(ml), _window(), 0.001, ptr(coef), None, ptr(dr), ptr(dmu), ptr(dlv), L.stream_ptr()))
     sync(L)
+    # the split form (level sums | scalars | gradient straight from the sums) gives the same bits
+    sums2 = torch.full((10,), float("nan"), dtype=torch.float64, device="cuda")
+    coef2, losses2, dr2 = torch.zeros_like(coef), torch.zeros_like(losses), torch.zeros_like(rd)
+    L.check(L.lib.cvae_loss_sums(B, ptr(rd), ptr(xd), _window(), ptr(sums2), L.stream_ptr()))
+    sync(L)
+    np.testing.assert_allclose(sums2.cpu().numpy(), sums.cpu().numpy(), rtol=1e-12)      # (double atomics: the order of the CTAs is free)
+    sums2.copy_(sums)
+    L.check(L.lib.cvae_loss_finalize(B, ptr(ml), None, ptr(sums2), 0.001, ptr(coef2), ptr(losses2), L.stream_ptr()))
+    L.check(L.lib.cvae_loss_bwd_sums(B, ptr(rd), ptr(xd), _window(), ptr(sums2), None, ptr(dr2), L.stream_ptr()))
+    sync(L)
+    assert torch.equal(losses, losses2) and torch.equal(coef, coef2) and torch.equal(dr, dr2)
     means = O.msssim_level_means(r, x)
     for l in range(5):
         n = B * 3 * (64 >> l) ** 2

@@ -1,4 +1,7 @@
-timeout 600 python -m pytest tests/test_kernels_misc.py tests/test_zz_fullsize.py -m gpu -q -x 2>&1 | tail -2
-timeout 300 python bench.py --steps 100 --warmup 5 --no-secondary 2>/dev/null | python -c "
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+run() { timeout 600 python bench.py --steps 300 --warmup 10 --no-secondary 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=1', d['value'], d['ms_per_step'], d['e2e']['value'])"
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])"; }
+echo "split"; run
+echo "no split"; CVAE_NO_LOSS_SPLIT=1 run
+echo "split"; run
