@@ -1,9 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/r02_bench_j.json 2> gpurun_out/r02_bench_j.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r02_bench_j.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','clocks','gpu_launches')})
-print('e2e', d['e2e']['value'], 'roofline', d['roofline']['frac'], d['roofline']['families'])
-g=d.get('gpu_baseline',{}); print('gpu_baseline best', g.get('best_ms_per_step'), g.get('speedup_vs_best_stock_pytorch'))
-PY
+timeout 300 python tools/profile_step.py 256 2 2>&1 | tail -1
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:"bottleneck|conv_wgrad" --launch-skip 11 -c 11 -o gpurun_out/prof_wg python tools/profile_step.py 256 2 > gpurun_out/ncu_wg.log 2>&1; tail -1 gpurun_out/ncu_wg.log
+python tools/ncu_summary.py gpurun_out/prof_wg.ncu-rep "Round 2 (final): weight-gradient GEMMs and the fused bottleneck kernels of one eager training step at batch 256 (ncu --set full)" > gpurun_out/r02_wgrad_bottleneck_full.md
+python tools/ncu_traffic.py gpurun_out/prof_wg.ncu-rep "x" | tail -8
+rm -f gpurun_out/prof_wg.ncu-rep
