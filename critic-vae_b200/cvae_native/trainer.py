@@ -94,6 +94,13 @@ class TrainStep:
         if from_u8:
             L.check(L.lib.cvae_frames_u8_to_f32(self.B, self.x_u8.data_ptr(), self.x.data_ptr(), s))
         side, joined = eng.side_stream, None
+        # CVAE_PACK_FIRST=1: the side stream packs the forward operand forms first (encoder conv 1 waits for them ~80 us into
+        # the step) and runs the critic after that (its value is needed ~250 us in).  Measured: device-timed step 1.343 ->
+        # 1.338 ms, but the end-to-end figure through the frame stager 192.9 k -> 190.3 k frames/s (profiles/r02_pack_first.log):
+        # the end-to-end number is the headline, so the critic stays in front by default.
+        packed_here = side is not None and os.environ.get("CVAE_PACK_FIRST") == "1"
+        if packed_here:
+            eng.pack()
         if self.critic_w is not None:
             if side is None:
                 L.check(L.lib.cvae_critic_fwd(self.B, self.x.data_ptr(), self.critic_w.data_ptr(), self.pred.data_ptr(), s))
@@ -107,7 +114,7 @@ class TrainStep:
                     joined = torch.cuda.Event()
                     joined.record()
         fused = eng.fused_bottleneck
-        eng.encode(self.x, True, ws, fc=not fused)
+        eng.encode(self.x, True, ws, pack=not packed_here, fc=not fused)
         if joined is not None:
             torch.cuda.current_stream().wait_event(joined)
         if fused:
